@@ -1,0 +1,291 @@
+// Device-resident path: plan / fields / step (Part 2 of include/fesom2-accelerate.h).
+// Rows are padded to an even pitch so every column starts 16-byte aligned and each thread moves
+// one double2 per array; a step is ten stage launches (mode 0) or two fused launches (mode 1),
+// optionally split into boundary / interior node sets around the NVLink halo exchange.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fesom2-accelerate.h"
+#include "fct_internal.h"
+
+namespace fct {
+
+enum RowKind { ROW_NODE, ROW_EDGE, ROW_ELEM };
+struct FieldMeta {
+    RowKind kind;
+    int width_minus;    // dense host row width = nl - width_minus   (UV_rhs: 2*(nl-1))
+    bool per_tracer;
+};
+static FieldMeta meta_of(int id)
+{
+    switch (id) {
+    case FCT_ADF_V: return {ROW_NODE, 0, true};
+    case FCT_AREA:
+    case FCT_AREA_INV: return {ROW_NODE, 0, false};
+    case FCT_HNODE:
+    case FCT_HNODE_NEW: return {ROW_NODE, 1, false};
+    case FCT_ADF_H:
+    case FCT_ADF_H_OUT: return {ROW_EDGE, 1, true};
+    case FCT_UV_RHS: return {ROW_ELEM, 1, true};
+    default: return {ROW_NODE, 1, true};
+    }
+}
+
+static inline Plan *P_(void **p)
+{
+    Plan *q = p ? static_cast<Plan *>(*p) : nullptr;
+    return (q && q->magic == PLAN_MAGIC) ? q : nullptr;
+}
+static inline Fields *F_(void **p)
+{
+    Fields *q = p ? static_cast<Fields *>(*p) : nullptr;
+    return (q && q->magic == FIELDS_MAGIC) ? q : nullptr;
+}
+static inline cudaStream_t S_(void **s)
+{
+    return (s && *s) ? *static_cast<cudaStream_t *>(*s) : (cudaStream_t)0;
+}
+
+static size_t field_rows(const Fields *f, RowKind k)
+{
+    return k == ROW_NODE ? f->rows : (k == ROW_EDGE ? (size_t)f->plan->G : (size_t)f->plan->E);
+}
+
+static Arrays arrays_of(const Fields *f, int mode, double dt, double eps, double big)
+{
+    Arrays A;
+    std::memset(&A, 0, sizeof(A));
+    A.ttf = f->buf[FCT_TTF];
+    A.lo = f->buf[FCT_LO];
+    A.adf_v = f->buf[FCT_ADF_V];
+    A.adf_h_in = f->buf[FCT_ADF_H];
+    A.adf_h_out = (mode == 1) ? f->buf[FCT_ADF_H_OUT] : f->buf[FCT_ADF_H];
+    A.ttf_max = f->buf[FCT_TTF_MAX];
+    A.ttf_min = f->buf[FCT_TTF_MIN];
+    A.plus = f->buf[FCT_PLUS];
+    A.minus = f->buf[FCT_MINUS];
+    A.del_v = f->buf[FCT_DEL_V];
+    A.del_h = f->buf[FCT_DEL_H];
+    A.uv_rhs = reinterpret_cast<double2 *>(f->buf[FCT_UV_RHS]);
+    A.ts_node = f->ts_node;
+    A.ts_nodev = f->ts_node;
+    A.ts_edge = f->ts_edge;
+    A.ts_uv = f->ts_uv;
+    A.area = f->buf[FCT_AREA];
+    A.area_inv = f->buf[FCT_AREA_INV];
+    A.hnode = f->buf[FCT_HNODE];
+    A.hnode_new = f->buf[FCT_HNODE_NEW];
+    A.pitchL = A.pitchV = A.pitchH = A.pitchU = f->P;
+    A.nl = f->plan->nl;
+    A.dt = dt;
+    A.eps = eps;
+    A.big = big;
+    return A;
+}
+
+static bool run_stage(Fields *f, const Arrays &A, int stage, const int *list, int first, int count, cudaStream_t s)
+{
+    return launch_stage(stage, 2, A, f->plan->dev, list, first, count, f->T, s);
+}
+
+}   // namespace fct
+
+using namespace fct;
+
+extern "C" {
+
+void fct_ale_plan_create_(void **plan, int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D,
+                          int *myDim_edge2D, int *nl, int *nlevels_nod2D, int *nlevels_elem2D,
+                          int *elem2D_nodes, int *nod_in_elem2D_num, int *nod_in_elem2D,
+                          int *nod_in_elem2D_dim, int *edges, int *edge_tri, int *istat)
+{
+    *plan = nullptr;
+    *istat = 1;
+    int ndev = 0;
+    if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount") || ndev < 1) return;
+    if (*nl < 3 || *nl > 0xffff) {
+        std::fprintf(stderr, "fesom2-accelerate: nl = %d out of range\n", *nl);
+        return;
+    }
+    Plan *p = create_plan_host(*myDim_nod2D, *eDim_nod2D, *myDim_elem2D, *myDim_edge2D, *nl, nlevels_nod2D,
+                               nlevels_elem2D, elem2D_nodes, nod_in_elem2D_num, nod_in_elem2D,
+                               *nod_in_elem2D_dim, edges, edge_tri);
+    if (!p) return;
+    *plan = p;
+    *istat = 0;
+}
+
+void fct_ale_plan_destroy_(void **plan, int *istat)
+{
+    Plan *p = P_(plan);
+    *istat = p ? 0 : 1;
+    if (p) destroy_plan(p);
+    if (plan) *plan = nullptr;
+}
+
+void fct_ale_plan_pitch_(void **plan, int *pitch)
+{
+    Plan *p = P_(plan);
+    *pitch = p ? p->pitch : 0;
+}
+
+void fct_ale_fields_create_(void **fields, void **plan, int *ntracers, int *with_uv_rhs, int *istat)
+{
+    *fields = nullptr;
+    *istat = 1;
+    Plan *p = P_(plan);
+    if (!p || *ntracers < 1) return;
+    Fields *f = new (std::nothrow) Fields;
+    if (!f) return;
+    f->plan = p;
+    f->T = *ntracers;
+    f->P = p->pitch;
+    f->rows = (size_t)p->N + p->H;
+    f->ts_node = f->rows * f->P;
+    f->ts_edge = (size_t)p->G * f->P;
+    f->ts_uv = (size_t)p->E * f->P;
+    bool ok = true;
+    for (int id = 0; id < FCT_FIELD_COUNT && ok; ++id) {
+        if (id == FCT_UV_RHS && !(with_uv_rhs && *with_uv_rhs)) continue;
+        const FieldMeta m = meta_of(id);
+        size_t n = field_rows(f, m.kind) * f->P * (m.per_tracer ? f->T : 1) * (id == FCT_UV_RHS ? 2 : 1);
+        n = n ? n : 1;
+        ok = cuda_ok(cudaMalloc(&f->buf[id], n * sizeof(double)), "cudaMalloc(fields)") &&
+             cuda_ok(cudaMemset(f->buf[id], 0, n * sizeof(double)), "cudaMemset(fields)");
+    }
+    if (!ok) {
+        for (double *b : f->buf)
+            if (b) cudaFree(b);
+        delete f;
+        return;
+    }
+    *fields = f;
+    *istat = 0;
+}
+
+void fct_ale_fields_destroy_(void **fields, int *istat)
+{
+    Fields *f = F_(fields);
+    *istat = f ? 0 : 1;
+    if (!f) return;
+    for (double *b : f->buf)
+        if (b) cudaFree(b);
+    f->magic = 0;
+    delete f;
+    *fields = nullptr;
+}
+
+static void field_copy(void **fields, int *field, int *tracer, real_type *host, void **stream, int *istat, bool up)
+{
+    *istat = 1;
+    Fields *f = F_(fields);
+    if (!f || *field < 0 || *field >= FCT_FIELD_COUNT || !f->buf[*field] || !host) return;
+    const FieldMeta m = meta_of(*field);
+    const int t = m.per_tracer ? *tracer : 0;
+    if (t < 0 || t >= f->T) return;
+    const size_t rows = field_rows(f, m.kind);
+    const size_t unit = (*field == FCT_UV_RHS) ? 2 : 1;
+    const size_t width = (size_t)(f->plan->nl - m.width_minus) * unit * sizeof(double);
+    const size_t pitch = (size_t)f->P * unit * sizeof(double);
+    double *d = f->buf[*field] + (size_t)t * rows * f->P * unit;
+    if (rows == 0) {
+        *istat = 0;
+        return;
+    }
+    cudaError_t e = up ? cudaMemcpy2DAsync(d, pitch, host, width, width, rows, cudaMemcpyHostToDevice, S_(stream))
+                       : cudaMemcpy2DAsync(host, width, d, pitch, width, rows, cudaMemcpyDeviceToHost, S_(stream));
+    *istat = cuda_ok(e, up ? "field upload" : "field download") ? 0 : 1;
+}
+
+void fct_ale_field_upload_(void **fields, int *field, int *tracer, real_type *host, void **stream, int *istat)
+{
+    field_copy(fields, field, tracer, host, stream, istat, true);
+}
+
+void fct_ale_field_download_(void **fields, int *field, int *tracer, real_type *host, void **stream, int *istat)
+{
+    field_copy(fields, field, tracer, host, stream, istat, false);
+}
+
+void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, real_type *flux_eps,
+                    real_type *bignumber, int *istat)
+{
+    *istat = 1;
+    Fields *f = F_(fields);
+    if (!f) return;
+    const Plan *p = f->plan;
+    const int st = *stage;
+    const Arrays A = arrays_of(f, st >= ST_PHASE_A ? 1 : 0, *dt, *flux_eps, *bignumber);
+    int count = p->N;
+    if (st == ST_A1) count = p->N + p->H;
+    else if (st == ST_A2) count = p->E;
+    else if (st == ST_B3H) count = p->G;
+    if (st == ST_A2 || st == ST_A3) {
+        if (!f->buf[FCT_UV_RHS]) {
+            std::fprintf(stderr, "fesom2-accelerate: stage %d needs fields created with UV_rhs\n", st);
+            return;
+        }
+    }
+    if (run_stage(f, A, st, nullptr, 0, count, S_(stream))) *istat = 0;
+}
+
+void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_type *dt,
+                   real_type *flux_eps, real_type *bignumber, int *alg_state)
+{
+    *alg_state = 0;
+    Fields *f = F_(fields);
+    if (!f) return;
+    const Plan *p = f->plan;
+    cudaStream_t s = S_(stream);
+    Halo *h = (halo && *halo) ? static_cast<Halo *>(*halo) : nullptr;
+    if (h && !halo_valid(h)) return;
+    const Arrays A = arrays_of(f, *mode, *dt, *flux_eps, *bignumber);
+    const int N = p->N;
+    if (*mode == 0) {
+        if (!f->buf[FCT_UV_RHS]) {
+            std::fprintf(stderr, "fesom2-accelerate: staged mode needs fields created with UV_rhs\n");
+            return;
+        }
+        static const int pre[6] = {ST_A1, ST_A2, ST_A3, ST_B1V, ST_B1H, ST_B2};
+        const int cnt[6] = {N + p->H, p->E, N, N, N, N};
+        for (int i = 0; i < 6; ++i) {
+            if (!run_stage(f, A, pre[i], nullptr, 0, cnt[i], s)) return;
+            *alg_state = i + 1;
+        }
+        if (h && !halo_exchange(f, h, s)) return;
+        static const int post[4] = {ST_B3V, ST_B3H, ST_CV, ST_CH};
+        const int cnt2[4] = {N, p->G, N, N};
+        for (int i = 0; i < 4; ++i) {
+            if (!run_stage(f, A, post[i], nullptr, 0, cnt2[i], s)) return;
+            *alg_state = 7 + i;
+        }
+        return;
+    }
+    if (!h) {
+        if (!run_stage(f, A, ST_PHASE_A, nullptr, 0, N, s)) return;
+        *alg_state = 6;
+        if (!run_stage(f, A, ST_PHASE_B, nullptr, 0, N, s)) return;
+        *alg_state = 10;
+        return;
+    }
+    // Overlapped schedule: the boundary nodes' factors are computed first and travel over NVLink
+    // on the halo's own stream while the interior nodes run phase A and phase B; the boundary
+    // nodes' phase B (the only consumer of remote factors) comes last.
+    cudaStream_t c = halo_comm_stream(h);
+    if (!run_stage(f, A, ST_PHASE_A, p->d_boundary, 0, p->n_boundary, s)) return;
+    if (!cuda_ok(cudaEventRecord(halo_event(h, 0), s), "event") ||
+        !cuda_ok(cudaStreamWaitEvent(c, halo_event(h, 0), 0), "wait"))
+        return;
+    if (!halo_exchange(f, h, c)) return;
+    if (!cuda_ok(cudaEventRecord(halo_event(h, 1), c), "event")) return;
+    if (!run_stage(f, A, ST_PHASE_A, p->d_interior, 0, p->n_interior, s)) return;
+    *alg_state = 6;
+    if (!run_stage(f, A, ST_PHASE_B, p->d_interior, 0, p->n_interior, s)) return;
+    if (!cuda_ok(cudaStreamWaitEvent(s, halo_event(h, 1), 0), "wait")) return;
+    if (!run_stage(f, A, ST_PHASE_B, p->d_boundary, 0, p->n_boundary, s)) return;
+    *alg_state = 10;
+}
+
+}   // extern "C"

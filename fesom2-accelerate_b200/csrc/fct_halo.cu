@@ -1,0 +1,190 @@
+// Halo exchange of fct_plus / fct_minus between mesh partitions (docs/refactoring.md:200, :235:
+// exchange_nod / exchange_nod_end, which the reference stages through the host and MPI).
+// Here both arrays stay on the device: one pack kernel gathers the boundary rows of all peers,
+// grouped ncclSend / ncclRecv move them over NVLink, and the receives land directly in the halo
+// rows (halo nodes are numbered grouped by owner, so no unpack is needed).
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/fesom2-accelerate.h"
+#include "fct_internal.h"
+
+namespace fct {
+
+struct Halo {
+    unsigned magic = HALO_MAGIC;
+    Plan *plan = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    std::vector<int> peers, send_off, send_cnt, recv_first, recv_cnt;
+    int total_send = 0;
+    int *d_send_nodes = nullptr;
+    double *sendbuf = nullptr;
+    size_t sendbuf_doubles = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+bool halo_valid(Halo *h) { return h && h->magic == HALO_MAGIC; }
+cudaStream_t halo_comm_stream(Halo *h) { return h->comm_stream; }
+cudaEvent_t halo_event(Halo *h, int which) { return h->ev[which]; }
+
+static bool nccl_ok(ncclResult_t r, const char *what)
+{
+    if (r != ncclSuccess) {
+        std::fprintf(stderr, "fesom2-accelerate: NCCL error \"%s\" in %s\n", ncclGetErrorString(r), what);
+        return false;
+    }
+    return true;
+}
+
+// sendbuf[((t*2 + a) * total + i) * P + z] = (a ? minus : plus)[t][send_nodes[i]][z]
+__global__ void k_halo_pack(const double *__restrict__ plus, const double *__restrict__ minus,
+                            const int *__restrict__ send_nodes, int total, int P, size_t ts_node,
+                            double *__restrict__ sendbuf)
+{
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    if (i >= total) return;
+    const int t = blockIdx.y;
+    const int z = threadIdx.x * 2;
+    if (z >= P) return;
+    const size_t src = t * ts_node + (size_t)__ldg(send_nodes + i) * P + z;
+    const double2 p = *reinterpret_cast<const double2 *>(plus + src);
+    const double2 m = *reinterpret_cast<const double2 *>(minus + src);
+    *reinterpret_cast<double2 *>(sendbuf + ((size_t)(t * 2 + 0) * total + i) * P + z) = p;
+    *reinterpret_cast<double2 *>(sendbuf + ((size_t)(t * 2 + 1) * total + i) * P + z) = m;
+}
+
+bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
+{
+    if (!halo_valid(h) || h->plan != f->plan) {
+        std::fprintf(stderr, "fesom2-accelerate: halo does not belong to these fields\n");
+        return false;
+    }
+    const int P = f->P, T = f->T;
+    const size_t need = (size_t)2 * T * h->total_send * P;
+    if (need > h->sendbuf_doubles) {
+        if (h->sendbuf) cudaFree(h->sendbuf);
+        h->sendbuf = nullptr;
+        h->sendbuf_doubles = 0;
+        if (!cuda_ok(cudaMalloc(&h->sendbuf, need * sizeof(double)), "cudaMalloc(halo)")) return false;
+        h->sendbuf_doubles = need;
+    }
+    double *plus = f->buf[FCT_PLUS], *minus = f->buf[FCT_MINUS];
+    if (h->total_send > 0) {
+        const int lx = P / 2;
+        const int ny = 256 / lx > 0 ? 256 / lx : 1;
+        dim3 block(lx, ny), grid((h->total_send + ny - 1) / ny, T);
+        k_halo_pack<<<grid, block, 0, s>>>(plus, minus, h->d_send_nodes, h->total_send, P, f->ts_node, h->sendbuf);
+        count_launch(1);
+        if (!cuda_ok(cudaGetLastError(), "halo pack")) return false;
+    }
+    if (!nccl_ok(ncclGroupStart(), "ncclGroupStart")) return false;
+    bool ok = true;
+    for (size_t k = 0; k < h->peers.size() && ok; ++k) {
+        const int peer = h->peers[k];
+        for (int t = 0; t < T && ok; ++t) {
+            for (int a = 0; a < 2 && ok; ++a) {
+                if (h->send_cnt[k] > 0)
+                    ok = nccl_ok(ncclSend(h->sendbuf + ((size_t)(t * 2 + a) * h->total_send + h->send_off[k]) * P,
+                                          (size_t)h->send_cnt[k] * P, ncclDouble, peer, h->comm, s), "ncclSend");
+                if (ok && h->recv_cnt[k] > 0)
+                    ok = nccl_ok(ncclRecv((a ? minus : plus) + t * f->ts_node + (size_t)h->recv_first[k] * P,
+                                          (size_t)h->recv_cnt[k] * P, ncclDouble, peer, h->comm, s), "ncclRecv");
+            }
+        }
+    }
+    ok = nccl_ok(ncclGroupEnd(), "ncclGroupEnd") && ok;
+    return ok;
+}
+
+}   // namespace fct
+
+using namespace fct;
+
+extern "C" {
+
+void fct_ale_comm_unique_id_(char *id128, int *istat)
+{
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    *istat = nccl_ok(ncclGetUniqueId(&id), "ncclGetUniqueId") ? 0 : 1;
+    if (*istat == 0) std::memcpy(id128, &id, 128);
+}
+
+void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int *nranks, int *npeers,
+                          int *peer_ranks, int *send_counts, int *send_nodes, int *recv_first,
+                          int *recv_counts, int *istat)
+{
+    *halo = nullptr;
+    *istat = 1;
+    Plan *p = plan ? static_cast<Plan *>(*plan) : nullptr;
+    if (!p || p->magic != PLAN_MAGIC) return;
+    Halo *h = new (std::nothrow) Halo;
+    if (!h) return;
+    h->plan = p;
+    h->rank = *rank;
+    h->nranks = *nranks;
+    int off = 0;
+    for (int k = 0; k < *npeers; ++k) {
+        h->peers.push_back(peer_ranks[k]);
+        h->send_off.push_back(off);
+        h->send_cnt.push_back(send_counts[k]);
+        h->recv_first.push_back(recv_first[k]);
+        h->recv_cnt.push_back(recv_counts[k]);
+        off += send_counts[k];
+    }
+    h->total_send = off;
+    bool ok = cuda_ok(cudaMalloc(&h->d_send_nodes, (size_t)(off > 0 ? off : 1) * sizeof(int)), "cudaMalloc(halo)");
+    if (ok && off > 0)
+        ok = cuda_ok(cudaMemcpy(h->d_send_nodes, send_nodes, (size_t)off * sizeof(int), cudaMemcpyHostToDevice), "H2D(halo)");
+    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking), "stream");
+    ok = ok && cuda_ok(cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming), "event");
+    ok = ok && cuda_ok(cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming), "event");
+    if (ok) {
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        ok = nccl_ok(ncclCommInitRank(&h->comm, *nranks, id, *rank), "ncclCommInitRank");
+    }
+    if (!ok) {
+        int st;
+        void *hp = h;
+        fct_ale_halo_destroy_(&hp, &st);
+        return;
+    }
+    *halo = h;
+    *istat = 0;
+}
+
+void fct_ale_halo_destroy_(void **halo, int *istat)
+{
+    Halo *h = (halo && *halo) ? static_cast<Halo *>(*halo) : nullptr;
+    *istat = 1;
+    if (!halo_valid(h)) return;
+    if (h->comm) ncclCommDestroy(h->comm);
+    if (h->d_send_nodes) cudaFree(h->d_send_nodes);
+    if (h->sendbuf) cudaFree(h->sendbuf);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    h->magic = 0;
+    delete h;
+    *halo = nullptr;
+    *istat = 0;
+}
+
+void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *istat)
+{
+    Fields *f = fields ? static_cast<Fields *>(*fields) : nullptr;
+    Halo *h = halo ? static_cast<Halo *>(*halo) : nullptr;
+    *istat = 1;
+    if (!f || f->magic != FIELDS_MAGIC || !halo_valid(h)) return;
+    cudaStream_t s = (stream && *stream) ? *static_cast<cudaStream_t *>(*stream) : (cudaStream_t)0;
+    if (halo_exchange(f, h, s)) *istat = 0;
+}
+
+}   // extern "C"

@@ -1,0 +1,46 @@
+// Declarations shared by the translation units of libfesom2-accelerate.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fct_kernels.cuh"
+#include "fct_plan.h"
+
+namespace fct {
+
+enum Stage {
+    ST_A1 = 0, ST_A2 = 1, ST_A3 = 2, ST_B1V = 3, ST_B1H = 4, ST_B2 = 5, ST_B3V = 6, ST_B3H = 7,
+    ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11
+};
+
+bool cuda_ok(cudaError_t e, const char *what);
+void count_launch(int n);
+bool launch_stage(int stage, int vec, const Arrays &A, const MeshDev &M, const int *list, int first,
+                  int count, int ntracers, cudaStream_t s);
+Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, const int *nlev_e,
+                       const int *elem_nodes, const int *nie_num, const int *nie, int nie_dim,
+                       const int *edges, const int *edge_tri);
+void destroy_plan(Plan *p);
+
+static const unsigned FIELDS_MAGIC = 0x464c4453u;
+static const unsigned HALO_MAGIC = 0x48414c4fu;
+static const unsigned PLAN_MAGIC = 0x504c414eu;
+
+struct Fields {
+    unsigned magic = FIELDS_MAGIC;
+    Plan *plan = nullptr;
+    int T = 0;         // tracers
+    int P = 0;         // row pitch (doubles)
+    size_t rows = 0;   // N + H
+    double *buf[16] = {nullptr};
+    size_t ts_node = 0, ts_edge = 0, ts_uv = 0;
+};
+
+struct Halo;
+// pack + send/recv of fct_plus / fct_minus on stream s (all tracers of f)
+bool halo_exchange(Fields *f, Halo *h, cudaStream_t s);
+// streams / events used to overlap the exchange with interior work
+cudaStream_t halo_comm_stream(Halo *h);
+cudaEvent_t halo_event(Halo *h, int which);
+bool halo_valid(Halo *h);
+
+}   // namespace fct

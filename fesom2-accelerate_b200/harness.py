@@ -1,0 +1,298 @@
+"""Host-side mirror of the reference's calling sequences, over the C ABI (ctypes).
+
+* `HandleChain` replays exactly what FESOM2's Fortran does per tracer step with the reference
+  library (/root/reference/src/fesom2-accelerate.cu:258-379):
+  transfer_mesh_ x7, alloc_var_, transfer_var_async_, fct_ale_pre_comm_acc_, await_stream_,
+  fct_ale_inter_comm_acc_, fct_ale_post_comm_acc_, plus the new fct_ale_c_acc_.
+* `DevicePlan` / `DeviceFields` / `HaloLink` drive the device-resident plan / fields / step ABI.
+
+This module plays the role of the reference's kernels/*.py drivers (argument set-up, run, fetch
+results) without kernel_tuner; checking against an answer is left to the tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import abi
+from .abi import cb, cd, ci, dptr, iptr
+from .mesh import Fields, Mesh, Partition
+
+
+class HandleChain:
+    NODE_L = ("ttf", "fct_LO", "hnode", "hnode_new", "del_ttf_advvert", "del_ttf_advhoriz",
+              "fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus")
+
+    def __init__(self, mesh: Mesh, fields: Fields, with_c: bool = True):
+        self.lib = abi.load()
+        abi.device_info()
+        self.m = mesh
+        self.f = fields
+        self.stream = abi.Stream()
+        m = mesh
+        self.mesh_vars = {k: abi.Var(np.ascontiguousarray(getattr(m, k)).reshape(-1), mesh=True)
+                          for k in ("nlevels_nod2D", "nlevels_elem", "elem2D_nodes",
+                                    "nod_in_elem2D_num", "nod_in_elem2D", "edges", "edge_tri")}
+        ev = ("ttf", "fct_adf_v", "fct_adf_h")     # pre_comm_acc waits on these upload events
+        names = ["ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area_inv", "fct_ttf_max", "fct_ttf_min",
+                 "fct_plus", "fct_minus"]
+        if with_c:
+            names += ["area", "hnode", "hnode_new", "del_ttf_advvert", "del_ttf_advhoriz"]
+        self.vars: Dict[str, abi.Var] = {}
+        for k in names:
+            self.vars[k] = abi.Var(getattr(fields, k).reshape(-1), event=k in ev)
+        # UV_rhs is a device-only scratch in the reference call sequence (reserve_var_)
+        self.vars["UV_rhs"] = abi.Var(size=mesh.myDim_elem2D * mesh.L * 2)
+        self.with_c = with_c
+        self.alg_state = C.c_int(0)
+        # outputs that only live on the device need one upload so untouched cells are defined
+        for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus"):
+            self.vars[k].upload()
+
+    def pre_comm(self):
+        m, f, v, mv, s = self.m, self.f, self.vars, self.mesh_vars, self.stream
+        for k in ("ttf", "fct_adf_v", "fct_adf_h"):
+            v[k].upload(stream=s, record=True)
+        v["area_inv"].upload(stream=s)
+        self.lib.fct_ale_pre_comm_acc_(
+            C.byref(self.alg_state), s.ref, v["fct_ttf_max"].ref, v["fct_ttf_min"].ref,
+            v["fct_plus"].ref, v["fct_minus"].ref, v["ttf"].ref, v["fct_LO"].ref, v["fct_adf_v"].ref,
+            v["fct_adf_h"].ref, v["UV_rhs"].ref, v["area_inv"].ref, ci(m.myDim_nod2D),
+            ci(m.eDim_nod2D), ci(m.myDim_elem2D), ci(m.myDim_edge2D), ci(m.nl),
+            mv["nlevels_nod2D"].ref, mv["nlevels_elem"].ref, mv["elem2D_nodes"].ref,
+            mv["nod_in_elem2D_num"].ref, mv["nod_in_elem2D"].ref, ci(m.nod_in_elem2D_dim),
+            mv["edges"].ref, mv["edge_tri"].ref, ci(f.vlimit), cd(f.flux_eps), cd(f.bignumber),
+            cd(f.dt))
+        return self.alg_state.value
+
+    def inter_comm(self):
+        m, v, mv, s = self.m, self.vars, self.mesh_vars, self.stream
+        self.lib.fct_ale_inter_comm_acc_(C.byref(self.alg_state), s.ref, v["fct_plus"].ref,
+                                         v["fct_minus"].ref, v["fct_adf_v"].ref, ci(m.myDim_nod2D),
+                                         ci(m.nl), mv["nlevels_nod2D"].ref)
+        return self.alg_state.value
+
+    def post_comm(self):
+        m, v, mv, s = self.m, self.vars, self.mesh_vars, self.stream
+        self.lib.fct_ale_post_comm_acc_(C.byref(self.alg_state), s.ref, v["fct_plus"].ref,
+                                        v["fct_minus"].ref, v["fct_adf_h"].ref, ci(m.myDim_edge2D),
+                                        ci(m.nl), mv["nlevels_elem"].ref, ci(m.nod_in_elem2D_dim),
+                                        mv["edges"].ref, mv["edge_tri"].ref)
+        return self.alg_state.value
+
+    def stage_c(self):
+        m, f, v, mv, s = self.m, self.f, self.vars, self.mesh_vars, self.stream
+        self.lib.fct_ale_c_acc_(C.byref(self.alg_state), s.ref, v["del_ttf_advvert"].ref,
+                                v["del_ttf_advhoriz"].ref, v["ttf"].ref, v["fct_LO"].ref,
+                                v["hnode"].ref, v["hnode_new"].ref, v["fct_adf_v"].ref,
+                                v["fct_adf_h"].ref, v["area"].ref, ci(m.myDim_nod2D),
+                                ci(m.myDim_edge2D), ci(m.nl), mv["nlevels_nod2D"].ref,
+                                mv["nlevels_elem"].ref, mv["edges"].ref, mv["edge_tri"].ref, cd(f.dt))
+        return self.alg_state.value
+
+    def step(self, exchange=None):
+        """One tracer step the way the Fortran drives the reference library; `exchange(fields)` is
+        the host-side MPI exchange_nod of fct_plus / fct_minus between the two awaits."""
+        st = self.pre_comm()
+        self.stream.sync()
+        if st != 6:
+            raise abi.AbiError(f"fct_ale_pre_comm_acc_ stopped at alg_state {st}")
+        self.inter_comm()           # overlaps the host exchange in the Fortran (md:203-235)
+        if exchange is not None:
+            exchange(self.f)
+        st = self.post_comm()
+        if st != 8:
+            raise abi.AbiError(f"fct_ale_post_comm_acc_ stopped at alg_state {st}")
+        if self.with_c:
+            st = self.stage_c()
+            if st != 10:
+                raise abi.AbiError(f"fct_ale_c_acc_ stopped at alg_state {st}")
+        self.stream.sync()
+        return st
+
+    def fetch(self, *names):
+        """Synchronous download of device-only results (fct_ttf_max/min, UV_rhs)."""
+        out = {}
+        for k in names:
+            if k == "UV_rhs":
+                host = np.empty((self.m.myDim_elem2D, self.m.L, 2))
+                out[k] = self.vars[k].download(host.reshape(-1)).reshape(host.shape)
+            else:
+                out[k] = self.vars[k].download().reshape(getattr(self.f, k).shape)
+        return out
+
+    def h2d_bytes(self):
+        v = self.vars
+        n = sum(v[k].host.nbytes for k in ("ttf", "fct_adf_v", "fct_adf_h", "area_inv", "fct_LO",
+                                           "fct_plus", "fct_minus"))
+        if self.with_c:
+            n += sum(v[k].host.nbytes for k in ("area", "hnode", "hnode_new", "del_ttf_advvert",
+                                                "del_ttf_advhoriz"))
+        return n
+
+    def d2h_bytes(self):
+        v = self.vars
+        n = sum(v[k].host.nbytes for k in ("fct_plus", "fct_minus", "fct_adf_v", "fct_adf_h"))
+        if self.with_c:
+            n += sum(v[k].host.nbytes for k in ("del_ttf_advvert", "del_ttf_advhoriz"))
+        return n
+
+    def free(self):
+        for v in list(self.vars.values()) + list(self.mesh_vars.values()):
+            v.free()
+        self.stream.free()
+
+
+class DevicePlan:
+    def __init__(self, mesh: Mesh):
+        self.lib = abi.load()
+        abi.device_info()
+        self.m = mesh
+        self.h = C.c_void_p()
+        st = C.c_int()
+        m = mesh
+        self.lib.fct_ale_plan_create_(
+            C.byref(self.h), ci(m.myDim_nod2D), ci(m.eDim_nod2D), ci(m.myDim_elem2D),
+            ci(m.myDim_edge2D), ci(m.nl), iptr(m.nlevels_nod2D), iptr(m.nlevels_elem),
+            iptr(m.elem2D_nodes.reshape(-1)), iptr(m.nod_in_elem2D_num),
+            iptr(m.nod_in_elem2D.reshape(-1)), ci(m.nod_in_elem2D_dim), iptr(m.edges.reshape(-1)),
+            iptr(m.edge_tri.reshape(-1)), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("fct_ale_plan_create_ failed (see stderr)")
+        p = C.c_int()
+        self.lib.fct_ale_plan_pitch_(C.byref(self.h), C.byref(p))
+        self.pitch = p.value
+
+    def free(self):
+        st = C.c_int()
+        self.lib.fct_ale_plan_destroy_(C.byref(self.h), C.byref(st))
+
+
+class HaloLink:
+    def __init__(self, plan: DevicePlan, part: Partition, unique_id: bytes):
+        self.lib = abi.load()
+        peers = sorted(set(part.send_lists) | set(part.recv_ranges))
+        send_counts = np.array([part.send_lists.get(p, np.empty(0, np.int32)).size for p in peers], np.int32)
+        send_nodes = np.concatenate([part.send_lists.get(p, np.empty(0, np.int32)) for p in peers]
+                                    + [np.empty(0, np.int32)]).astype(np.int32)
+        recv_first = np.array([part.recv_ranges.get(p, (0, 0))[0] for p in peers], np.int32)
+        recv_counts = np.array([part.recv_ranges.get(p, (0, 0))[1] for p in peers], np.int32)
+        peers_a = np.array(peers, np.int32)
+        if send_nodes.size == 0:
+            send_nodes = np.zeros(1, np.int32)
+        pad = lambda a: a if a.size else np.zeros(1, np.int32)
+        self.h = C.c_void_p()
+        st = C.c_int()
+        idbuf = C.create_string_buffer(unique_id, 128)
+        self.lib.fct_ale_halo_create_(C.byref(self.h), C.byref(plan.h), idbuf, ci(part.rank),
+                                      ci(part.nparts), ci(len(peers)), iptr(pad(peers_a)),
+                                      iptr(pad(send_counts)), iptr(send_nodes), iptr(pad(recv_first)),
+                                      iptr(pad(recv_counts)), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("fct_ale_halo_create_ failed (see stderr)")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        st = C.c_int()
+        abi.load().fct_ale_comm_unique_id_(buf, C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("fct_ale_comm_unique_id_ failed")
+        return buf.raw
+
+    def free(self):
+        st = C.c_int()
+        self.lib.fct_ale_halo_destroy_(C.byref(self.h), C.byref(st))
+
+
+class DeviceFields:
+    """A batch of tracers resident on the device."""
+    PER_TRACER = ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "del_ttf_advvert", "del_ttf_advhoriz",
+                  "fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus")
+    STATIC = ("area", "area_inv", "hnode", "hnode_new")
+
+    def __init__(self, plan: DevicePlan, ntracers: int = 1, with_uv: bool = True):
+        self.lib = abi.load()
+        self.plan = plan
+        self.T = ntracers
+        self.with_uv = with_uv
+        self.h = C.c_void_p()
+        st = C.c_int()
+        self.lib.fct_ale_fields_create_(C.byref(self.h), C.byref(plan.h), ci(ntracers),
+                                        ci(1 if with_uv else 0), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("fct_ale_fields_create_ failed (out of device memory?)")
+        self.stream = abi.Stream()
+
+    def _copy(self, fn, name, tracer, host):
+        st = C.c_int()
+        fn(C.byref(self.h), ci(abi.FIELD_IDS[name]), ci(tracer), dptr(host.reshape(-1)), self.stream.ref,
+           C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError(f"transfer of {name} failed")
+
+    def upload_field(self, name: str, host: np.ndarray, tracer: int = 0):
+        self._copy(self.lib.fct_ale_field_upload_, name, tracer, host)
+
+    def download_field(self, name: str, host: np.ndarray, tracer: int = 0):
+        self._copy(self.lib.fct_ale_field_download_, name, tracer, host)
+
+    def upload(self, f: Fields, tracer: int = 0, static: bool = True, outputs: bool = True):
+        names = ["ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "del_ttf_advvert", "del_ttf_advhoriz"]
+        if outputs:
+            names += ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus"]
+            if self.with_uv and f.UV_rhs is not None:
+                names.append("UV_rhs")
+        if static:
+            names += list(self.STATIC)
+        for k in names:
+            self.upload_field(k, getattr(f, k), tracer)
+        if outputs:
+            self.upload_field("fct_adf_h_out", f.fct_adf_h, tracer)
+        self.stream.sync()
+
+    def download(self, f: Fields, tracer: int = 0, mode: int = 1, names=None) -> Fields:
+        """Fetch results into (a copy of) `f`; the limited horizontal fluxes come from the OUT
+        buffer in fused mode."""
+        out = f.copy()
+        if names is None:
+            names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v",
+                     "del_ttf_advvert", "del_ttf_advhoriz"]
+            if mode == 0 and self.with_uv and f.UV_rhs is not None:
+                names.append("UV_rhs")
+        for k in names:
+            self.download_field(k, getattr(out, k), tracer)
+        self.download_field("fct_adf_h_out" if mode == 1 else "fct_adf_h", out.fct_adf_h, tracer)
+        self.stream.sync()
+        return out
+
+    def step(self, f: Fields, mode: int = 1, halo: Optional[HaloLink] = None, sync: bool = True) -> int:
+        st = C.c_int()
+        hp = C.byref(halo.h) if halo is not None else None
+        self.lib.fct_ale_step_(C.byref(self.h), hp, self.stream.ref, ci(mode), cd(f.dt),
+                               cd(f.flux_eps), cd(f.bignumber), C.byref(st))
+        if sync:
+            self.stream.sync()
+        return st.value
+
+    def stage(self, name: str, f: Fields, sync: bool = True):
+        st = C.c_int()
+        self.lib.fct_ale_stage_(C.byref(self.h), self.stream.ref, ci(abi.STAGE_IDS[name]), cd(f.dt),
+                                cd(f.flux_eps), cd(f.bignumber), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError(f"stage {name} failed")
+        if sync:
+            self.stream.sync()
+
+    def exchange(self, halo: HaloLink):
+        st = C.c_int()
+        self.lib.fct_ale_halo_exchange_(C.byref(self.h), C.byref(halo.h), self.stream.ref, C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("halo exchange failed")
+
+    def free(self):
+        st = C.c_int()
+        self.lib.fct_ale_fields_destroy_(C.byref(self.h), C.byref(st))
+        self.stream.free()

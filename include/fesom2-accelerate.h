@@ -1,0 +1,243 @@
+/*
+ * fesom2-accelerate.h -- C ABI of the B200-native fct_ale tracer limiter.
+ *
+ * Drop-in boundary.  Part 1 re-declares, binary-compatibly, every symbol FESOM2's Fortran binds
+ * through ISO_C_BINDING in the reference library (each entry cites the reference interface it
+ * replaces as <reference file>:<line>).  Part 2 is new ABI that the reference lacks (SURVEY.md
+ * section 8b): stage c on the device, release calls, and a device-resident plan / fields / step /
+ * halo interface used by the fused two-kernel path and by the multi-GPU runs.
+ *
+ * Conventions, identical to the reference (include/fesom2-accelerate.h:128-236 there):
+ *   - extern "C", gfortran-style lower-case names with a trailing underscore;
+ *   - every argument by pointer, scalars included; opaque handles travel as void** (the address
+ *     of a Fortran type(c_ptr));
+ *   - real_type is double; connectivity is 1-based int32;
+ *   - status through int* istat (0 ok, 1 failed / fell back) and int* alg_state (last completed
+ *     stage); errors are also printed on stderr; no call throws or aborts;
+ *   - the *_acc_ calls are asynchronous on the caller's stream: await_stream_ before touching the
+ *     host copies.
+ *   - There is no CPU fallback anywhere: without a CUDA device every compute call reports failure.
+ *
+ * Layout of the arrays behind the handles (reference src/reference.cpp:309-334, :396, :419):
+ *   L = nl-1.  node fields [node*L + z]; fct_adf_v, area, area_inv [node*nl + z];
+ *   fct_adf_h [edge*L + z]; UV_rhs [(elem*L + z)*2 + {0:max,1:min}].
+ */
+#ifndef FESOM2_ACCELERATE_B200_H
+#define FESOM2_ACCELERATE_B200_H
+
+#include <stddef.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+typedef double real_type; /* reference include/fesom2-accelerate.h:10 */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 1: the reference's symbols                                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Leading members are the reference's struct gpuMemory (include/fesom2-accelerate.h:19-28), so
+ * the legacy gpuMemory* entry points stay binary compatible; the tail is ours. */
+struct gpuMemory {
+    void *host_pointer;
+    void *device_pointer;
+    size_t size;      /* bytes */
+    void *event;      /* cudaEvent_t; valid only when has_event != 0 */
+    int has_event;
+    int event_recorded;
+    unsigned magic;
+};
+
+/* replaces set_mpi_rank_  (include/fesom2-accelerate.h:146, src/fesom2-accelerate.cu:206) */
+void set_mpi_rank_(int *rank, int *total_ranks);
+/* replaces transfer_mesh_ (include :147, src :114): allocate *size int32 and upload synchronously */
+void transfer_mesh_(void **ret, int *host_ptr, int *size, int *istat);
+/* replaces alloc_var_ (include :148, src :129): *size doubles bound to host_ptr, no upload */
+void alloc_var_(void **ret, real_type *host_ptr, int *size, bool *create_event, int *istat);
+/* replaces reserve_var_ (include :149, src :136): device-only buffer */
+void reserve_var_(void **ret, int *size, bool *create_event, int *istat);
+/* replaces allocate_pinned_doubles_ (include :150, src :143); falls back to malloc with istat=1 */
+void allocate_pinned_doubles_(void **hostptr, int *size, int *istat);
+/* replaces transfer_var_ (include :151, src :156): rebind host pointer, synchronous upload */
+void transfer_var_(void **mem, real_type *host_ptr);
+/* replaces transfer_var_async_ (include :152, src :163) */
+void transfer_var_async_(void **mem, real_type *host_ptr, void **stream, bool *record_event);
+/* replace make_stream_ / await_stream_ (include :153-154, src :170, :188) */
+void make_stream_(void **stream, int *istat);
+void await_stream_(void **s, int *istat);
+
+/* replaces fct_ale_pre_comm_acc_ (include :156, src :258-340): uploads fct_LO, waits on the upload
+ * events of ttf / fct_adf_v / fct_adf_h, runs a1..b2, downloads fct_plus / fct_minus
+ * asynchronously; *alg_state = 6. */
+void fct_ale_pre_comm_acc_(int *alg_state, void **s, void **fct_ttf_max, void **fct_ttf_min,
+                           void **fct_plus, void **fct_minus, void **ttf, void **fct_LO,
+                           void **fct_adf_v, void **fct_adf_h, void **UV_rhs, void **area_inv,
+                           int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D, int *myDim_edge2D,
+                           int *nl, void **nlevels_nod2D, void **nlevels_elem2D, void **elem2D_nodes,
+                           void **nod_in_elem2D_num, void **nod_in_elem2D, int *nod_in_elem2D_dim,
+                           void **nod2D_edges, void **elem2D_edges, int *vlimit, real_type *flux_eps,
+                           real_type *bignumber, real_type *dt);
+/* replaces fct_ale_inter_comm_acc_ (include :157, src :342-356): b3 vertical, downloads fct_adf_v;
+ * *alg_state = 7 */
+void fct_ale_inter_comm_acc_(int *alg_state, void **s, void **fct_plus, void **fct_minus,
+                             void **fct_adf_v, int *myDim_nod2D, int *nl, void **nlevels_nod2D);
+/* replaces fct_ale_post_comm_acc_ (include :158, src :358-379): re-uploads the halo-updated
+ * fct_plus / fct_minus, b3 horizontal, downloads fct_adf_h; *alg_state = 8.  The 8th argument is
+ * the ELEMENT depth array, as in the reference's definition (src :369). */
+void fct_ale_post_comm_acc_(int *alg_state, void **s, void **fct_plus, void **fct_minus,
+                            void **fct_adf_h, int *myDim_edge2D, int *nl, void **nlevels_elem2D,
+                            int *nod_in_elem2D_dim, void **nod2D_edges, void **elem2D_edges);
+
+/* replace fct_ale_a1_accelerated / a2 / a1_a2 (include :173, :189, :209; src :42, :69, :91):
+ * synchronous (or stream-async) copies around single launches.  The reference gives the trailing
+ * two parameters C++ default values; C callers pass them explicitly. */
+void fct_ale_a1_accelerated(const int maxLevels, const int nNodes, struct gpuMemory *nLevels_nod2D,
+                            struct gpuMemory *fct_ttf_max, struct gpuMemory *fct_ttf_min,
+                            struct gpuMemory *fct_low_order, struct gpuMemory *ttf, bool synchronous,
+                            void *stream);
+void fct_ale_a2_accelerated(const int maxLevels, const int nElements, struct gpuMemory *nLevels_elem,
+                            struct gpuMemory *elementNodes, struct gpuMemory *UV_rhs,
+                            struct gpuMemory *fct_ttf_max, struct gpuMemory *fct_ttf_min,
+                            bool synchronous, void *stream);
+void fct_ale_a1_a2_accelerated(const int maxLevels, const int nNodes, const int nElements,
+                               struct gpuMemory *nLevels_nod2D, struct gpuMemory *nLevels_elem,
+                               struct gpuMemory *elementNodes, struct gpuMemory *fct_ttf_max,
+                               struct gpuMemory *fct_ttf_min, struct gpuMemory *fct_low_order,
+                               struct gpuMemory *ttf, struct gpuMemory *UV_rhs, bool synchronous,
+                               void *stream);
+
+/* replace fct_ale_a{1,2,3,4}_reference_ and fct_ale_pre_comm_ (include :142, :225-235;
+ * src/reference.cpp:289-438).  Same names, arguments (HOST arrays) and results, but computed on
+ * the GPU: each call uploads its inputs, runs the corresponding stage kernels and downloads the
+ * outputs synchronously.  a3 includes b1 vertical and a4 is b1 horizontal + b2, as there. */
+void fct_ale_a1_reference_(int *nNodes, int *nLevels_nod2D, int *nl, real_type *fct_ttf_max,
+                           real_type *fct_ttf_min, real_type *fct_low_order, real_type *ttf);
+void fct_ale_a2_reference_(int *nElements, int *nLevels_elem2D, int *nl, real_type *UV_rhs,
+                           int *elem2D_nodes, real_type *fct_ttf_max, real_type *fct_ttf_min,
+                           real_type *bignumber);
+void fct_ale_a3_reference_(int *nNodes2D, int *nLevels_nod2D, int *nl, real_type *fct_ttf_max,
+                           real_type *fct_ttf_min, real_type *fct_LO, real_type *UV_rhs,
+                           real_type *fct_plus, real_type *fct_minus, real_type *fct_adf_v,
+                           int *nod_in_elem2D, int *nod_in_elem2D_num, int *nod_in_elem2D_dim);
+void fct_ale_a4_reference_(int *nNodes2D, int *nLevels_nod2D, int *nLevels_elem2D, int *nl,
+                           int *nEdges2D, real_type *fct_plus, real_type *fct_minus,
+                           real_type *fct_adf_h, real_type *area_inv, real_type *fct_ttf_max,
+                           real_type *fct_ttf_min, int *edges, int *edge_tri, real_type *flux_eps,
+                           real_type *dt);
+void fct_ale_pre_comm_(int *alg_state, real_type *fct_ttf_max, real_type *fct_ttf_min,
+                       real_type *fct_plus, real_type *fct_minus, real_type *ttf, real_type *fct_LO,
+                       real_type *fct_adf_v, real_type *fct_adf_h, real_type *UV_rhs,
+                       real_type *area_inv, int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D,
+                       int *myDim_edge2D, int *nl, int *nlevels_nod2D, int *nlevels_elem2D,
+                       int *elem2D_nodes, int *nod_in_elem2D_num, int *nod_in_elem2D,
+                       int *nod_in_elem2D_dim, int *nod2D_edges, int *elem2D_edges, int *vlimit,
+                       real_type *flux_eps, real_type *bignumber, real_type *dt);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 2: new ABI (absent from the reference; SURVEY.md section 8b "New ABI")                  */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Stage c on the device (the reference leaves docs/refactoring.md:292-314 to the Fortran CPU
+ * code; its kernels/fct_ale_c_*.cu are built but never launched).  Handle-based like the calls
+ * above; area / hnode / hnode_new / del_* are uploaded from their bound host pointers first,
+ * del_ttf_advvert / del_ttf_advhoriz are downloaded asynchronously after; *alg_state = 10. */
+void fct_ale_c_acc_(int *alg_state, void **s, void **del_ttf_advvert, void **del_ttf_advhoriz,
+                    void **ttf, void **fct_LO, void **hnode, void **hnode_new, void **fct_adf_v,
+                    void **fct_adf_h, void **area, int *myDim_nod2D, int *myDim_edge2D, int *nl,
+                    void **nlevels_nod2D, void **nlevels_elem2D, void **nod2D_edges,
+                    void **elem2D_edges, real_type *dt);
+
+/* synchronous / asynchronous download of a variable into host_ptr (rebinds the host pointer) */
+void transfer_var_back_(void **mem, real_type *host_ptr);
+void transfer_var_back_async_(void **mem, real_type *host_ptr, void **stream);
+/* release calls the reference never had */
+void free_var_(void **mem, int *istat);
+void free_pinned_doubles_(void **hostptr, int *istat);
+void free_stream_(void **stream, int *istat);
+/* 0: one kernel per reference stage (default, materialises UV_rhs); 1: fused phase kernels */
+void fct_ale_set_fused_(int *fused);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+void fct_ale_launch_count_(long long *count);
+/* name and compute capability of the bound device; istat=1 when there is none */
+void fct_ale_device_info_(char *name64, int *cc_major, int *cc_minor, int *sm_count, int *istat);
+
+/* CUDA-event timing on the caller's stream (bench.py, the harness): create / record / elapsed */
+void fct_ale_event_create_(void **event, int *istat);
+void fct_ale_event_record_(void **event, void **stream, int *istat);
+void fct_ale_event_elapsed_ms_(void **start, void **stop, real_type *ms, int *istat);
+void fct_ale_event_destroy_(void **event, int *istat);
+/* free / total bytes of device memory on the bound device */
+void fct_ale_mem_info_(long long *free_bytes, long long *total_bytes, int *istat);
+
+/* ---- device-resident path: plan (mesh + derived gather lists), fields, step ---------------- */
+
+/* Build the per-mesh plan from HOST connectivity (1-based, as the Fortran holds it): uploads the
+ * mesh, derives the node->neighbour list (a1+a2+a3 without UV_rhs), the node->edge gather list in
+ * ascending edge order (deterministic replacement of the b1h / c_h atomics) and the
+ * boundary / interior node split used to overlap the halo exchange. */
+void fct_ale_plan_create_(void **plan, int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D,
+                          int *myDim_edge2D, int *nl, int *nlevels_nod2D, int *nlevels_elem2D,
+                          int *elem2D_nodes, int *nod_in_elem2D_num, int *nod_in_elem2D,
+                          int *nod_in_elem2D_dim, int *edges, int *edge_tri, int *istat);
+void fct_ale_plan_destroy_(void **plan, int *istat);
+/* pitch (in doubles) of every padded device row of this plan: nl rounded up to an even count */
+void fct_ale_plan_pitch_(void **plan, int *pitch);
+
+/* Device arrays for a batch of *ntracers tracers on a plan, rows padded to the plan pitch.
+ * *with_uv_rhs != 0 also allocates UV_rhs (needed by the staged mode only). */
+void fct_ale_fields_create_(void **fields, void **plan, int *ntracers, int *with_uv_rhs, int *istat);
+void fct_ale_fields_destroy_(void **fields, int *istat);
+
+/* Field identifiers for upload / download */
+enum fct_field_id {
+    FCT_TTF = 0, FCT_LO = 1, FCT_ADF_V = 2, FCT_ADF_H = 3, FCT_AREA = 4, FCT_AREA_INV = 5,
+    FCT_HNODE = 6, FCT_HNODE_NEW = 7, FCT_DEL_V = 8, FCT_DEL_H = 9, FCT_TTF_MAX = 10,
+    FCT_TTF_MIN = 11, FCT_PLUS = 12, FCT_MINUS = 13, FCT_UV_RHS = 14, FCT_ADF_H_OUT = 15,
+    FCT_FIELD_COUNT = 16
+};
+/* dense host array (the Fortran layout above) <-> padded device rows of tracer *tracer
+ * (mesh-static fields area / area_inv / hnode / hnode_new ignore *tracer).  Asynchronous on
+ * *stream; host memory should be pinned for the copy to overlap. */
+void fct_ale_field_upload_(void **fields, int *field, int *tracer, real_type *host, void **stream,
+                           int *istat);
+void fct_ale_field_download_(void **fields, int *field, int *tracer, real_type *host, void **stream,
+                             int *istat);
+
+/* One fct_ale step a1..c over all tracers of `fields`, everything resident on the device.
+ *   *mode 0: ten stage kernels (one per reference kernel);  *mode 1: two fused phase kernels.
+ * When `halo` is non-null the fct_plus / fct_minus halo exchange runs between b2 and b3
+ * horizontal over NVLink, overlapped with the interior nodes' phase B work.
+ * The limited horizontal fluxes are written to the FCT_ADF_H_OUT buffer in mode 1 (the in-place
+ * update of the reference would race between the two end nodes of an edge) and in place
+ * (FCT_ADF_H) in mode 0.  *alg_state = 10 on success. */
+void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_type *dt,
+                   real_type *flux_eps, real_type *bignumber, int *alg_state);
+/* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,
+ * 6 b3v, 7 b3h, 8 c_v, 9 c_h; 10 fused phase A, 11 fused phase B */
+void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, real_type *flux_eps,
+                    real_type *bignumber, int *istat);
+
+/* ---- multi-GPU halo exchange of fct_plus / fct_minus (docs/refactoring.md:200, :235) ------- */
+
+/* 128-byte NCCL unique id, created on one rank and handed to the others by the caller (MPI in
+ * FESOM2, torch.distributed's store in bench.py). */
+void fct_ale_comm_unique_id_(char *id128, int *istat);
+/* Per-rank halo descriptor.  send_nodes: concatenated 0-based local owned node ids, send_counts[p]
+ * of them for peer_ranks[p], in the order of the receiver's halo numbering; the rows received from
+ * peer p land in local nodes [recv_first[p], recv_first[p]+recv_counts[p]) (halo nodes are grouped
+ * by owner). */
+void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int *nranks, int *npeers,
+                          int *peer_ranks, int *send_counts, int *send_nodes, int *recv_first,
+                          int *recv_counts, int *istat);
+void fct_ale_halo_destroy_(void **halo, int *istat);
+/* the exchange alone (tests, timing) */
+void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *istat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FESOM2_ACCELERATE_B200_H */

@@ -1,0 +1,245 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Bar (BASELINE.json north_star): fct_ttf_max / fct_ttf_min bit-exact; limited fluxes and
+tracer increments within 1e-12 relative -- the kernels keep the oracle's operation order and are
+built with -fmad=false, so these tests demand (and get) bit equality everywhere."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12          # relative, fluxes and increments (north_star)
+OUT_KEYS = ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "fct_adf_h",
+            "del_ttf_advvert", "del_ttf_advhoriz")
+
+
+def check(got, want, keys=OUT_KEYS, exact=True, owned=None):
+    for k in keys:
+        a, b = getattr(got, k), getattr(want, k)
+        if owned is not None and k != "fct_adf_h":
+            a, b = a[:owned], b[:owned]
+        if k in ("fct_ttf_max", "fct_ttf_min") or exact:
+            assert bits_equal(a, b), f"{k}: max rel err {rel_err(a, b, 1e-30):.3e}"
+        else:
+            assert rel_err(a, b, floor=1e-30) <= TOL, k
+
+
+def cases(mesh_mod, name):
+    if name == "adversarial":
+        return mesh_mod.adversarial_case(300, 17, seed=5)
+    if name == "adversarial_even":
+        return mesh_mod.adversarial_case(257, 16, seed=6)
+    m = mesh_mod.make_workload(name)
+    return m, mesh_mod.make_fields(m)
+
+
+@pytest.mark.parametrize("name", ["tiny", "pi", "adversarial", "adversarial_even"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_handle_abi_chain(mesh_mod, harness, abi, oracle_mod, name, fused):
+    """The reference's own call sequence (transfer_var_async_ -> pre_comm_acc -> inter -> post ->
+    c_acc) on dense host arrays."""
+    m, f = cases(mesh_mod, name)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    got = f.copy()
+    abi.set_fused(fused)
+    try:
+        ch = harness.HandleChain(m, got)
+        assert ch.step() == 10
+        dev = ch.fetch("fct_ttf_max", "fct_ttf_min", "UV_rhs")
+        ch.free()
+    finally:
+        abi.set_fused(False)
+    check(got, want)
+    if not fused:
+        assert bits_equal(dev["UV_rhs"], want.UV_rhs)
+
+
+@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "adversarial", "adversarial_even"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
+    m, f = cases(mesh_mod, name)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    plan = harness.DevicePlan(m)
+    assert plan.pitch % 2 == 0 and plan.pitch >= m.nl
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(f)
+    assert df.step(f, mode=mode) == 10
+    got = df.download(f, mode=mode)
+    check(got, want)
+    if mode == 0:
+        assert bits_equal(got.UV_rhs, want.UV_rhs)
+    df.free()
+    plan.free()
+
+
+def test_stage_by_stage(mesh_mod, harness, oracle_mod):
+    """Each stage kernel against the oracle stage it replaces (the reference's NUM_KERNELS staged
+    execution, src/fesom2-accelerate.cu:256-335)."""
+    m, f = cases(mesh_mod, "pi")
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(f)
+    want = f.copy()
+    for name, fn in oracle_mod.STAGES:
+        fn(m, want)
+        df.stage(name, f)
+        got = df.download(f, mode=0)
+        check(got, want)
+        assert bits_equal(got.UV_rhs, want.UV_rhs), name
+    df.free()
+    plan.free()
+
+
+def test_reference_named_entry_points(abi, oracle_mod):
+    """fct_ale_a{1,2,3,4}_reference_ / fct_ale_pre_comm_ keep the reference's names and host-array
+    signatures but run on the GPU; checked against the golden vectors of src/reference.cpp."""
+    import ctypes as C
+    lib = abi.load()
+    for case in ("ref_cpp_tiny", "ref_cpp_adversarial"):
+        m, f, z = load_golden(case)
+        g = f.copy()
+        st = C.c_int(-1)
+        lib.fct_ale_pre_comm_(
+            C.byref(st), abi.dptr(g.fct_ttf_max.reshape(-1)), abi.dptr(g.fct_ttf_min.reshape(-1)),
+            abi.dptr(g.fct_plus.reshape(-1)), abi.dptr(g.fct_minus.reshape(-1)), abi.dptr(g.ttf.reshape(-1)),
+            abi.dptr(g.fct_LO.reshape(-1)), abi.dptr(g.fct_adf_v.reshape(-1)), abi.dptr(g.fct_adf_h.reshape(-1)),
+            abi.dptr(g.UV_rhs.reshape(-1)), abi.dptr(g.area_inv.reshape(-1)), abi.ci(m.myDim_nod2D),
+            abi.ci(m.eDim_nod2D), abi.ci(m.myDim_elem2D), abi.ci(m.myDim_edge2D), abi.ci(m.nl),
+            abi.iptr(m.nlevels_nod2D), abi.iptr(m.nlevels_elem), abi.iptr(m.elem2D_nodes.reshape(-1)),
+            abi.iptr(m.nod_in_elem2D_num), abi.iptr(m.nod_in_elem2D.reshape(-1)), abi.ci(m.nod_in_elem2D_dim),
+            abi.iptr(m.edges.reshape(-1)), abi.iptr(m.edge_tri.reshape(-1)), abi.ci(1), abi.cd(g.flux_eps),
+            abi.cd(g.bignumber), abi.cd(g.dt))
+        assert st.value == 5          # alg_state of reference.cpp:302
+        assert bits_equal(g.UV_rhs, z["a2_UV_rhs"])
+        assert bits_equal(g.fct_ttf_max, z["a3_fct_ttf_max"])
+        assert bits_equal(g.fct_ttf_min, z["a3_fct_ttf_min"])
+        assert bits_equal(g.fct_plus, z["a4_fct_plus"])
+        assert bits_equal(g.fct_minus, z["a4_fct_minus"])
+
+
+def test_golden_b3_c_on_gpu(harness):
+    """b3 / c kernels against the golden vectors of the reference's numpy reference() functions."""
+    m, f, z = load_golden("ref_numpy_tiny")
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(f)
+    for s in ("b3v", "b3h", "cv", "ch"):
+        df.stage(s, f)
+    got = df.download(f, mode=0)
+    assert bits_equal(got.fct_adf_v, z["b3v_fct_adf_v"])
+    assert bits_equal(got.fct_adf_h, z["b3h_fct_adf_h"])
+    assert rel_err(got.del_ttf_advvert, z["cv_del_ttf_advvert"], floor=1.0) < TOL
+    assert rel_err(got.del_ttf_advhoriz, z["ch_del_ttf_advhoriz"], floor=1.0) < TOL
+    df.free()
+    plan.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_multi_tracer_batch(mesh_mod, harness, oracle_mod, mode):
+    """T, S + passive tracers in one launch (BASELINE.json config 5, reduced to 3 tracers on pi)."""
+    m = mesh_mod.make_workload("pi")
+    T = 3
+    fs = [mesh_mod.make_fields(m, seed=1 + t) for t in range(T)]
+    for t in range(1, T):       # mesh-static fields are shared by all tracers
+        for k in ("area", "area_inv", "hnode", "hnode_new"):
+            setattr(fs[t], k, fs[0].__dict__[k])
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, T, with_uv=True)
+    for t in range(T):
+        df.upload(fs[t], tracer=t, static=(t == 0))
+    assert df.step(fs[0], mode=mode) == 10
+    for t in range(T):
+        want = fs[t].copy()
+        oracle_mod.fct_ale(m, want)
+        check(df.download(fs[t], tracer=t, mode=mode), want)
+    df.free()
+    plan.free()
+
+
+def test_step_is_repeatable_and_deterministic(mesh_mod, harness):
+    """No atomics anywhere: two runs from the same inputs give identical bits."""
+    m, f = cases(mesh_mod, "core2")
+    plan = harness.DevicePlan(m)
+    outs = []
+    for _ in range(2):
+        df = harness.DeviceFields(plan, 1, with_uv=False)
+        df.upload(f)
+        assert df.step(f, mode=1) == 10
+        outs.append(df.download(f, mode=1))
+        df.free()
+    check(outs[0], outs[1])
+    plan.free()
+
+
+@pytest.mark.parametrize("nparts", [2, 5])
+def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts):
+    """Every partition of a mesh run on this GPU with the halo exchange emulated through the host:
+    owned results of all partitions must reproduce the single-domain oracle bit for bit (boundary /
+    interior node lists, halo numbering, cut edges duplicated on both sides)."""
+    m, f = cases(mesh_mod, "pi")
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    parts = mesh_mod.partition_mesh(m, nparts)
+    plans = [harness.DevicePlan(p.mesh) for p in parts]
+    lfs = [mesh_mod.slice_fields(f, p) for p in parts]
+    dfs = [harness.DeviceFields(pl, 1, with_uv=False) for pl in plans]
+    for df, lf in zip(dfs, lfs):
+        df.upload(lf)
+        df.stage("phaseA", lf)
+    # exchange_nod(fct_plus, fct_minus) through the host
+    gplus = np.empty_like(f.fct_plus)
+    gminus = np.empty_like(f.fct_minus)
+    for p, df, lf in zip(parts, dfs, lfs):
+        n = p.mesh.myDim_nod2D
+        tmp = df.download(lf, mode=1, names=["fct_plus", "fct_minus"])
+        gplus[p.mesh.node_gid[:n]] = tmp.fct_plus[:n]
+        gminus[p.mesh.node_gid[:n]] = tmp.fct_minus[:n]
+    for p, df, lf in zip(parts, dfs, lfs):
+        df.upload_field("fct_plus", np.ascontiguousarray(gplus[p.mesh.node_gid]))
+        df.upload_field("fct_minus", np.ascontiguousarray(gminus[p.mesh.node_gid]))
+        df.stream.sync()
+        df.stage("phaseB", lf)
+    got = f.copy()
+    for p, df, lf in zip(parts, dfs, lfs):
+        n = p.mesh.myDim_nod2D
+        o = df.download(lf, mode=1)
+        for k in OUT_KEYS:
+            if k == "fct_adf_h":
+                # an edge is written by exactly one of its owned end nodes on each rank that holds it
+                got.fct_adf_h[p.mesh.edge_gid] = o.fct_adf_h
+            else:
+                getattr(got, k)[p.mesh.node_gid[:n]] = getattr(o, k)[:n]
+    check(got, want)
+    for df in dfs:
+        df.free()
+    for pl in plans:
+        pl.free()
+
+
+def test_full_size_properties(mesh_mod, harness):
+    """DART-depth columns (nl = 80) at a size the oracle would take long on: size-independent
+    properties of the limiter + determinism."""
+    m = mesh_mod.make_mesh(1024, 780, 80, seed=0)
+    f = mesh_mod.make_fields(m, seed=2, with_uv=False, poison=False)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=False)
+    df.upload(f)
+    assert df.step(f, mode=1) == 10
+    g = df.download(f, mode=1)
+    L = m.L
+    act = np.arange(L)[None, :] < (m.nlevels_nod2D[:, None] - 1)
+    assert g.fct_plus[act].max() <= 1.0 and g.fct_minus[act].max() <= 1.0
+    assert (g.fct_plus[act] >= 0).all() and (g.fct_minus[act] >= 0).all()
+    assert (np.abs(g.fct_adf_v) <= np.abs(f.fct_adf_v)).all()
+    assert (np.abs(g.fct_adf_h) <= np.abs(f.fct_adf_h)).all()
+    assert (g.fct_adf_v * f.fct_adf_v >= 0).all() and (g.fct_adf_h * f.fct_adf_h >= 0).all()
+    for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz"):
+        assert bits_equal(getattr(g, k)[~act], getattr(f, k)[~act]), k
+    # conservation: the horizontal increments of an edge cancel when weighted with area/dt
+    w = (g.del_ttf_advhoriz - f.del_ttf_advhoriz) * f.area[:, :L]
+    assert abs(w[act].sum()) <= 1e-9 * np.abs(w[act]).sum()
+    df.free()
+    plan.free()

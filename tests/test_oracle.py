@@ -1,0 +1,91 @@
+"""CPU: pin the oracle (oracle/fct_ale_oracle.c) against the reference's own code.
+
+* golden vectors produced by src/reference.cpp (a1..a4) and by the reference's numpy reference()
+  functions (b3 / c) -- tests/golden/make_golden.py;
+* live comparison with oracle/_ref/libref.so (the reference compiled unmodified) when present.
+"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, load_golden, rel_err
+
+
+@pytest.mark.parametrize("case", ["ref_cpp_tiny", "ref_cpp_adversarial"])
+def test_oracle_matches_reference_cpp_golden(oracle_mod, case):
+    m, f, z = load_golden(case)
+    g = f.copy()
+    oracle_mod.a1(m, g)
+    assert bits_equal(g.fct_ttf_max, z["a1_fct_ttf_max"])
+    assert bits_equal(g.fct_ttf_min, z["a1_fct_ttf_min"])
+    oracle_mod.a2(m, g)
+    assert bits_equal(g.UV_rhs, z["a2_UV_rhs"])
+    oracle_mod.a3(m, g)
+    oracle_mod.b1_vertical(m, g)
+    for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus"):
+        assert bits_equal(getattr(g, k), z["a3_" + k]), k
+    oracle_mod.b1_horizontal(m, g)
+    oracle_mod.b2(m, g)
+    assert bits_equal(g.fct_plus, z["a4_fct_plus"])
+    assert bits_equal(g.fct_minus, z["a4_fct_minus"])
+
+
+def test_oracle_b3_c_match_reference_numpy_golden(oracle_mod):
+    """b3 bit-exact (pure compare/select/multiply); c within 1e-12 relative: the numpy twin groups
+    x*(dt/area) where the Fortran (and the oracle) group (x*dt)/area."""
+    m, f, z = load_golden("ref_numpy_tiny")
+    g = f.copy()      # state after the reference's a1..a4
+    oracle_mod.b3_vertical(m, g)
+    assert bits_equal(g.fct_adf_v, z["b3v_fct_adf_v"])
+    oracle_mod.b3_horizontal(m, g)
+    assert bits_equal(g.fct_adf_h, z["b3h_fct_adf_h"])
+    oracle_mod.c_vertical(m, g)
+    oracle_mod.c_horizontal(m, g)
+    tol = 1e-12
+    assert rel_err(g.del_ttf_advvert, z["cv_del_ttf_advvert"], floor=1.0) < tol
+    assert rel_err(g.del_ttf_advhoriz, z["ch_del_ttf_advhoriz"], floor=1.0) < tol
+    # something actually moved
+    assert not bits_equal(g.del_ttf_advvert, f.del_ttf_advvert)
+    assert not bits_equal(g.fct_adf_h, f.fct_adf_h)
+
+
+@pytest.mark.parametrize("name", ["tiny", "pi"])
+def test_oracle_matches_libref_live(oracle_mod, mesh_mod, name):
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    m = mesh_mod.make_workload(name)
+    f = mesh_mod.make_fields(m)
+    a, b = f.copy(), f.copy()
+    oracle_mod.pre_comm(m, a)
+    oracle_mod.ref_pre_comm(m, b)
+    for k in ("fct_ttf_max", "fct_ttf_min", "UV_rhs", "fct_plus", "fct_minus"):
+        assert bits_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_oracle_matches_libref_adversarial(oracle_mod, mesh_mod):
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    for seed in range(4):
+        m, f = mesh_mod.adversarial_case(200, 20, seed=seed)
+        a, b = f.copy(), f.copy()
+        oracle_mod.pre_comm(m, a)
+        oracle_mod.ref_pre_comm(m, b)
+        for k in ("fct_ttf_max", "fct_ttf_min", "UV_rhs", "fct_plus", "fct_minus"):
+            assert bits_equal(getattr(a, k), getattr(b, k)), (seed, k)
+
+
+def test_limiter_properties(oracle_mod, mesh_mod):
+    """Domain properties the GPU tests reuse at full size: factors in (-inf, 1], limited fluxes never
+    grow and keep their sign, bottom vertical flux untouched, inactive cells untouched."""
+    m = mesh_mod.make_workload("pi")
+    f = mesh_mod.make_fields(m)
+    g = f.copy()
+    oracle_mod.fct_ale(m, g)
+    L = m.L
+    act = np.arange(L)[None, :] < (m.nlevels_nod2D[:, None] - 1)
+    assert g.fct_plus[act].max() <= 1.0 and g.fct_minus[act].max() <= 1.0
+    assert (g.fct_plus[act] >= 0).all() and (g.fct_minus[act] >= 0).all()
+    assert (np.abs(g.fct_adf_v) <= np.abs(f.fct_adf_v)).all()
+    assert (np.abs(g.fct_adf_h) <= np.abs(f.fct_adf_h)).all()
+    assert (g.fct_adf_v * f.fct_adf_v >= 0).all()
+    for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz"):
+        assert bits_equal(getattr(g, k)[~act], getattr(f, k)[~act]), k
