@@ -22,7 +22,7 @@ SYMBOLS = [
     "fct_ale_a1_reference_", "fct_ale_a2_reference_", "fct_ale_a3_reference_",
     "fct_ale_a4_reference_", "fct_ale_pre_comm_",
     "fct_ale_c_acc_", "transfer_var_back_", "transfer_var_back_async_", "free_var_",
-    "free_pinned_doubles_", "free_stream_", "fct_ale_set_fused_", "fct_ale_launch_count_",
+    "free_pinned_doubles_", "free_stream_", "fct_ale_set_fused_", "fct_ale_tune_", "fct_ale_launch_count_",
     "fct_ale_device_info_", "fct_ale_event_create_", "fct_ale_event_record_",
     "fct_ale_event_elapsed_ms_", "fct_ale_event_destroy_", "fct_ale_mem_info_",
     "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_",
@@ -37,7 +37,8 @@ FIELD_IDS = dict(ttf=0, fct_LO=1, fct_adf_v=2, fct_adf_h=3, area=4, area_inv=5, 
                  hnode_new=7, del_ttf_advvert=8, del_ttf_advhoriz=9, fct_ttf_max=10, fct_ttf_min=11,
                  fct_plus=12, fct_minus=13, UV_rhs=14, fct_adf_h_out=15)
 STAGE_IDS = dict(a1=0, a2=1, a3=2, b1v=3, b1h=4, b2=5, b3v=6, b3h=7, cv=8, ch=9, phaseA=10,
-                 phaseB=11)
+                 phaseB=11, phaseA_tile=12, phaseB_tile=13, phaseA_tile_boundary=14,
+                 phaseA_tile_interior=15, phaseB_tile_boundary=16, phaseB_tile_interior=17)
 
 
 class GpuMemory(C.Structure):
@@ -106,6 +107,11 @@ def launch_count() -> int:
 
 def set_fused(flag: bool) -> None:
     load().fct_ale_set_fused_(ci(1 if flag else 0))
+
+
+def tune(name: str, value: int) -> None:
+    """Tuning knob FCT_<name> (see the header); never changes results."""
+    load().fct_ale_tune_(C.c_char_p(name.encode()), ci(value))
 
 
 # --------------------------------------------------------------------------------------------

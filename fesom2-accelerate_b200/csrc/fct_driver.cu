@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 #include <tuple>
 #include <vector>
 
@@ -186,6 +187,140 @@ static bool upload_derived(Plan *p, const DerivedHost &d)
            p->d_boundary && p->d_interior;
 }
 
+// ---------------------------------------------------------------------------------------------
+// tile-staged fused kernels: plan tables, launch
+// ---------------------------------------------------------------------------------------------
+// tuning knobs: fct_ale_tune_("NAME", value) overrides the environment variable FCT_NAME
+static std::map<std::string, int> g_tune;
+static std::mutex g_tune_mutex;
+static int env_int(const char *name, int dflt)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_tune_mutex);
+        auto it = g_tune.find(name);
+        if (it != g_tune.end()) return it->second;
+    }
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+void set_tune(const char *name, int value)
+{
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    g_tune[std::string("FCT_") + name] = value;
+}
+
+static const size_t TILE_SMEM_CAP = 113 * 1024;   // at least two CTAs per SM
+
+static bool upload_tileset(Plan *p, const TileSetHost &h, int TN, int TE, TileDev &T)
+{
+    T.row_off = upload_vec(p, h.row_off);
+    T.rows = upload_vec(p, h.rows);
+    T.hdr = upload_vec(p, h.hdr);
+    T.work_off = upload_vec(p, h.work_off);
+    T.ent = upload_vec(p, h.ent);
+    T.TN = TN;
+    T.TE = TE;
+    T.max_rows = h.max_rows;
+    T.ntiles = h.ntiles;
+    return T.row_off && T.rows && T.hdr && T.work_off && T.ent;
+}
+
+static void build_plan_tiles(Plan *p, const DerivedHost &d, const int *nlev_n)
+{
+    p->tiles_ok = false;
+    if (env_int("FCT_TILE", 1) == 0) return;
+    const int verbose = env_int("FCT_VERBOSE", 0);
+    int TE = 1;
+    for (int n = 0; n < p->N; ++n) TE = std::max(TE, d.edg_off[n + 1] - d.edg_off[n]);
+    if (TE > 16) {
+        if (verbose) std::fprintf(stderr, "fesom2-accelerate: a node has %d edges: using the untiled fused kernels\n", TE);
+        return;
+    }
+    const std::vector<int> *lists[3] = {nullptr, &d.boundary, &d.interior};
+    const int nsets = p->H > 0 ? 3 : 1;
+    // the two phases want different tile sizes: phase A is issue-bound and prefers many small
+    // CTAs per SM, phase B amortises its staging over larger patches (measured, profiles/)
+    for (int ph = 0; ph < 2; ++ph) {
+        const int TN = std::max(1, env_int(ph == 0 ? "FCT_TILE_NODES_A" : "FCT_TILE_NODES_B", env_int("FCT_TILE_NODES", ph == 0 ? 12 : 24)));
+        const int iters = std::max(1, env_int(ph == 0 ? "FCT_TILE_ITERS_A" : "FCT_TILE_ITERS_B", env_int("FCT_TILE_ITERS", ph == 0 ? 1 : 2)));
+        TileSetHost h[3];
+        for (int s = 0; s < nsets; ++s) {
+            if (!build_tileset(d, nlev_n, p->N, p->N + p->H, lists[s], TN, TE, 2, TILE_THREADS, iters * TILE_THREADS, h[s])) {
+                if (verbose) std::fprintf(stderr, "fesom2-accelerate: mesh is not a plain triangulation: using the untiled fused kernels\n");
+                return;
+            }
+            const size_t smem = tile_smem_bytes(ph == 0, p->pitch, TN, TE, h[s].max_rows);
+            if (smem > TILE_SMEM_CAP) {
+                if (verbose)
+                    std::fprintf(stderr, "fesom2-accelerate: tile needs %d rows (%zu B smem): using the untiled fused kernels\n",
+                                 h[s].max_rows, smem);
+                return;
+            }
+        }
+        for (int s = 0; s < nsets; ++s)
+            if (!upload_tileset(p, h[s], TN, TE, p->tiles[ph][s])) return;
+        if (verbose)
+            std::fprintf(stderr, "fesom2-accelerate: phase %c: %d tiles of <= %d nodes, <= %d staged rows, %d entries/node, %zu B smem\n",
+                         ph == 0 ? 'A' : 'B', h[0].ntiles, TN, h[0].max_rows, TE, tile_smem_bytes(ph == 0, p->pitch, TN, TE, h[0].max_rows));
+    }
+    p->tiles_ok = true;
+}
+
+typedef void (*tile_kern_t)(Arrays, TileDev);
+
+// Variants of the tile kernels: HB edge-flux rows loaded ahead per item, MINB resident CTAs the
+// register allocation is bounded for.  FCT_TILE_VARIANT_A / _B select one (tuning knob).
+struct TileVariant {
+    tile_kern_t fn;
+    const char *name;
+};
+static const TileVariant g_variants_a[] = {
+    {k_phaseA_tile<2, 8, 3>, "hb8-min3"}, {k_phaseA_tile<2, 0, 4>, "hb0-min4"}, {k_phaseA_tile<2, 4, 3>, "hb4-min3"},
+    {k_phaseA_tile<2, 8, 2>, "hb8-min2"}, {k_phaseA_tile<2, 0, 3>, "hb0-min3"}, {k_phaseA_tile<2, 6, 4>, "hb6-min4"},
+};
+static const TileVariant g_variants_b[] = {
+    {k_phaseB_tile<2, 8, 2>, "hb8-min2"}, {k_phaseB_tile<2, 0, 3>, "hb0-min3"}, {k_phaseB_tile<2, 4, 3>, "hb4-min3"},
+    {k_phaseB_tile<2, 8, 3>, "hb8-min3"}, {k_phaseB_tile<2, 4, 2>, "hb4-min2"}, {k_phaseB_tile<2, 6, 3>, "hb6-min3"},
+};
+
+// which: 0 all owned nodes, 1 boundary list, 2 interior list
+bool launch_tile(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s)
+{
+    const bool isA = stage == ST_PHASE_A;
+    TileDev T = p->tiles[isA ? 0 : 1][which];
+    if (T.ntiles <= 0) return true;
+    const int ai = isA ? 0 : 1;
+    constexpr int NV = 6;
+    static size_t attr_set[2][NV] = {};
+    static size_t occ_smem[2][NV] = {};
+    static int resident[2][NV] = {};
+    const int vi = std::min(std::max(env_int(isA ? "FCT_TILE_VARIANT_A" : "FCT_TILE_VARIANT_B", 0), 0), NV - 1);
+    const TileVariant &v = isA ? g_variants_a[vi] : g_variants_b[vi];
+    const size_t smem = tile_smem_bytes(isA, A.pitchL, T.TN, T.TE, T.max_rows);
+    if (smem > attr_set[ai][vi]) {
+        if (!cuda_ok(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute"))
+            return false;
+        attr_set[ai][vi] = smem;
+    }
+    if (smem != occ_smem[ai][vi]) {
+        // tables of the tile one "resident wave" ahead are prefetched into L2
+        int per_sm = 0, dev_id = 0, sms = 0;
+        cudaGetDevice(&dev_id);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, TILE_THREADS, smem) != cudaSuccess) per_sm = 2;
+        resident[ai][vi] = std::max(per_sm, 1) * std::max(sms, 1);
+        occ_smem[ai][vi] = smem;
+        if (env_int("FCT_VERBOSE", 0))
+            std::fprintf(stderr, "fesom2-accelerate: phase %c tile kernel %s: %zu B smem, %d CTAs/SM\n",
+                         isA ? 'A' : 'B', v.name, smem, per_sm);
+    }
+    T.ahead = env_int("FCT_TILE_AHEAD", resident[ai][vi]);
+    dim3 grid(T.ntiles, ntracers, 1);
+    v.fn<<<grid, TILE_THREADS, smem, s>>>(A, T);
+    count_launch(1);
+    return cuda_ok(cudaGetLastError(), "tile kernel launch");
+}
+
 void destroy_plan(Plan *p)
 {
     if (!p) return;
@@ -223,6 +358,7 @@ Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, co
         destroy_plan(p);
         return nullptr;
     }
+    build_plan_tiles(p, d, nlev_n);
     return p;
 }
 
@@ -872,6 +1008,11 @@ void free_stream_(void **stream, int *istat)
 }
 
 void fct_ale_set_fused_(int *fused) { g_fused.store(fused && *fused ? 1 : 0); }
+
+void fct_ale_tune_(const char *name, int *value)
+{
+    if (name && value) set_tune(name, *value);
+}
 
 void fct_ale_launch_count_(long long *count) { *count = g_launches.load(); }
 

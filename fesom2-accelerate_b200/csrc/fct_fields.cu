@@ -61,7 +61,7 @@ static Arrays arrays_of(const Fields *f, int mode, double dt, double eps, double
     A.lo = f->buf[FCT_LO];
     A.adf_v = f->buf[FCT_ADF_V];
     A.adf_h_in = f->buf[FCT_ADF_H];
-    A.adf_h_out = (mode == 1) ? f->buf[FCT_ADF_H_OUT] : f->buf[FCT_ADF_H];
+    A.adf_h_out = (mode >= 1) ? f->buf[FCT_ADF_H_OUT] : f->buf[FCT_ADF_H];
     A.ttf_max = f->buf[FCT_TTF_MAX];
     A.ttf_min = f->buf[FCT_TTF_MIN];
     A.plus = f->buf[FCT_PLUS];
@@ -218,6 +218,22 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     const Plan *p = f->plan;
     const int st = *stage;
     const Arrays A = arrays_of(f, st >= ST_PHASE_A ? 1 : 0, *dt, *flux_eps, *bignumber);
+    if (st >= ST_PHASE_A_TILE && st <= 17) {
+        // 12/13: all owned nodes; 14/15: phase A on the boundary / interior list; 16/17: phase B
+        if (!p->tiles_ok) {
+            std::fprintf(stderr, "fesom2-accelerate: this plan has no tiles\n");
+            return;
+        }
+        const int which = st <= ST_PHASE_B_TILE ? 0 : 1 + ((st - 14) & 1);
+        const int phase = st <= ST_PHASE_B_TILE ? (st == ST_PHASE_A_TILE ? ST_PHASE_A : ST_PHASE_B)
+                                                : (st < 16 ? ST_PHASE_A : ST_PHASE_B);
+        if (which != 0 && p->H == 0) {
+            std::fprintf(stderr, "fesom2-accelerate: boundary / interior tiles exist on partitioned plans only\n");
+            return;
+        }
+        if (launch_tile(phase, A, p, which, f->T, S_(stream))) *istat = 0;
+        return;
+    }
     int count = p->N;
     if (st == ST_A1) count = p->N + p->H;
     else if (st == ST_A2) count = p->E;
@@ -263,10 +279,18 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
         }
         return;
     }
+    const bool tiled = p->tiles_ok && *mode == 1;
+    // one fused phase over a node set: 0 all owned, 1 boundary, 2 interior
+    auto phase = [&](int stage, int which) -> bool {
+        if (tiled) return launch_tile(stage, A, p, which, f->T, s);
+        if (which == 0) return run_stage(f, A, stage, nullptr, 0, N, s);
+        return which == 1 ? run_stage(f, A, stage, p->d_boundary, 0, p->n_boundary, s)
+                          : run_stage(f, A, stage, p->d_interior, 0, p->n_interior, s);
+    };
     if (!h) {
-        if (!run_stage(f, A, ST_PHASE_A, nullptr, 0, N, s)) return;
+        if (!phase(ST_PHASE_A, 0)) return;
         *alg_state = 6;
-        if (!run_stage(f, A, ST_PHASE_B, nullptr, 0, N, s)) return;
+        if (!phase(ST_PHASE_B, 0)) return;
         *alg_state = 10;
         return;
     }
@@ -274,17 +298,17 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
     // on the halo's own stream while the interior nodes run phase A and phase B; the boundary
     // nodes' phase B (the only consumer of remote factors) comes last.
     cudaStream_t c = halo_comm_stream(h);
-    if (!run_stage(f, A, ST_PHASE_A, p->d_boundary, 0, p->n_boundary, s)) return;
+    if (!phase(ST_PHASE_A, 1)) return;
     if (!cuda_ok(cudaEventRecord(halo_event(h, 0), s), "event") ||
         !cuda_ok(cudaStreamWaitEvent(c, halo_event(h, 0), 0), "wait"))
         return;
     if (!halo_exchange(f, h, c)) return;
     if (!cuda_ok(cudaEventRecord(halo_event(h, 1), c), "event")) return;
-    if (!run_stage(f, A, ST_PHASE_A, p->d_interior, 0, p->n_interior, s)) return;
+    if (!phase(ST_PHASE_A, 2)) return;
     *alg_state = 6;
-    if (!run_stage(f, A, ST_PHASE_B, p->d_interior, 0, p->n_interior, s)) return;
+    if (!phase(ST_PHASE_B, 2)) return;
     if (!cuda_ok(cudaStreamWaitEvent(s, halo_event(h, 1), 0), "wait")) return;
-    if (!run_stage(f, A, ST_PHASE_B, p->d_boundary, 0, p->n_boundary, s)) return;
+    if (!phase(ST_PHASE_B, 1)) return;
     *alg_state = 10;
 }
 

@@ -9,13 +9,16 @@ namespace fct {
 
 enum Stage {
     ST_A1 = 0, ST_A2 = 1, ST_A3 = 2, ST_B1V = 3, ST_B1H = 4, ST_B2 = 5, ST_B3V = 6, ST_B3H = 7,
-    ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11
+    ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11, ST_PHASE_A_TILE = 12, ST_PHASE_B_TILE = 13
 };
 
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(int n);
 bool launch_stage(int stage, int vec, const Arrays &A, const MeshDev &M, const int *list, int first,
                   int count, int ntracers, cudaStream_t s);
+// tile-staged fused phase (stage = ST_PHASE_A / ST_PHASE_B) over node set `which`:
+// 0 all owned nodes, 1 boundary list, 2 interior list
+bool launch_tile(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s);
 Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, const int *nlev_e,
                        const int *elem_nodes, const int *nie_num, const int *nie, int nie_dim,
                        const int *edges, const int *edge_tri);

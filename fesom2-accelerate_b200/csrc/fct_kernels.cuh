@@ -435,7 +435,7 @@ __global__ void k_b3h(Arrays A, MeshDev M, const int *list, int first, int count
     stv<VEC>(A.adf_h_out + ho, h, min(VEC, dg - it.z0));
 }
 
-// c vertical -- docs/refactoring.md:295-300 (Fortran grouping ((x*dt)/area))
+// c vertical -- docs/refactoring.md:295-300, flux term grouped x*(dt/area) as kernels/fct_ale_c_vertical.cu:12
 template <int VEC>
 __global__ void k_cv(Arrays A, MeshDev M, const int *list, int first, int count)
 {
@@ -457,7 +457,7 @@ __global__ void k_cv(Arrays A, MeshDev M, const int *list, int first, int count)
     for (int v = 0; v <= VEC; ++v) f[v] = (it.z0 + v <= nz) ? vrow[it.z0 + v] : 0.0;
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
-        d[v] = d[v] - t[v] * hn[v] + l[v] * hw[v] + (f[v] - f[v + 1]) * A.dt / ar[v];
+        d[v] = d[v] - t[v] * hn[v] + l[v] * hw[v] + (f[v] - f[v + 1]) * (A.dt / ar[v]);
     stv<VEC>(A.del_v + off, d, min(VEC, nz - it.z0));
 }
 
@@ -475,6 +475,8 @@ __global__ void k_ch(Arrays A, MeshDev M, const int *list, int first, int count)
     double d[VEC], ar[VEC];
     ldv<VEC>(A.del_h + off, d);
     ldv_ro<VEC>(A.area + (size_t)n * A.pitchV + it.z0, ar);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) ar[v] = A.dt / ar[v];   // dt/area once per cell (fct_ale_c_horizontal.cu:25)
     const double *hb = A.adf_h_out + blockIdx.y * A.ts_edge + it.z0;
     const int b = __ldg(M.edg_off + n), e = __ldg(M.edg_off + n + 1);
     for (int k = b; k < e; ++k) {
@@ -487,7 +489,7 @@ __global__ void k_ch(Arrays A, MeshDev M, const int *list, int first, int count)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 if (it.z0 + v < dg) {
-                    const double x = h[v] * A.dt / ar[v];
+                    const double x = h[v] * ar[v];
                     d[v] = second ? d[v] - x : d[v] + x;
                 }
             }
@@ -626,7 +628,10 @@ __global__ void k_phaseB(Arrays A, MeshDev M, const int *list, int first, int co
         ldv_ro<VEC>(A.minus + off, mn);
 #pragma unroll
         for (int v = 0; v < VEC; ++v)
-            dv[v] = dv[v] - t[v] * hn[v] + l[v] * hw[v] + (fl[v] - fl[v + 1]) * A.dt / ar[v];
+            ar[v] = A.dt / ar[v];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            dv[v] = dv[v] - t[v] * hn[v] + l[v] * hw[v] + (fl[v] - fl[v + 1]) * ar[v];
 
         const double *hb = A.adf_h_in + blockIdx.y * A.ts_edge + z0;
         double *ho = A.adf_h_out + blockIdx.y * A.ts_edge + z0;
@@ -647,7 +652,7 @@ __global__ void k_phaseB(Arrays A, MeshDev M, const int *list, int first, int co
                     if (z0 + v < dg) {
                         h[v] = second ? b3h_point(h[v], po[v], mo[v], pn[v], mn[v])
                                       : b3h_point(h[v], pn[v], mn[v], po[v], mo[v]);
-                        const double x = h[v] * A.dt / ar[v];
+                        const double x = h[v] * ar[v];
                         dh[v] = second ? dh[v] - x : dh[v] + x;
                     }
                 }

@@ -103,4 +103,91 @@ bool build_derived(int N, int H, int E, int G, int nl, const int *nlev_e, const 
     return true;
 }
 
+bool build_tileset(const DerivedHost &d, const int *nlev_n, int N, int NT, const std::vector<int> *list,
+                   int TN, int TE, int vec, int threads, int budget, TileSetHost &out)
+{
+    const int count = list ? (int)list->size() : N;
+    out = TileSetHost();
+    out.row_off.assign(1, 0);
+    std::vector<int> stamp((size_t)NT, -1), local((size_t)NT, 0);
+    std::vector<int> tile_nodes, tile_wo;
+    std::vector<std::pair<int, int>> a, b;
+    int pos = 0, tile = 0;
+    while (pos < count) {
+        // ---- pick the nodes of this tile ----
+        tile_nodes.clear();
+        tile_wo.clear();
+        int items = 0;
+        while (pos < count && (int)tile_nodes.size() < TN) {
+            const int n = list ? (*list)[pos] : pos;
+            const int nz = std::max(nlev_n[n] - 1, 0);
+            const int ch = (nz + vec - 1) / vec;
+            if (ch > threads) return false;
+            int start = items;
+            if (ch > 0 && start / threads != (start + ch - 1) / threads) start = (start / threads + 1) * threads;
+            if (start + ch > budget && !tile_nodes.empty()) break;
+            tile_nodes.push_back(n);
+            tile_wo.push_back(start);
+            items = start + ch;
+            ++pos;
+        }
+        const int nt = (int)tile_nodes.size();
+        for (int i = 0; i < nt; ++i) {
+            stamp[tile_nodes[i]] = tile;
+            local[tile_nodes[i]] = i;
+            out.rows.push_back(make_int2(tile_nodes[i], std::max(nlev_n[tile_nodes[i]] - 1, 0)));
+        }
+        // ---- headers, gather lists, halo rows ----
+        int nrows = nt;
+        for (int i = 0; i < TN; ++i) {
+            if (i >= nt) {
+                out.hdr.push_back(make_int4(-1, 0, 0, 0));
+                out.work_off.push_back(items);
+                for (int k = 0; k < TE; ++k) out.ent.push_back(make_int4(0, 0, 0, 0));
+                continue;
+            }
+            const int n = tile_nodes[i];
+            const int nb0 = d.nbr_off[n], nb1 = d.nbr_off[n + 1];
+            const int e0 = d.edg_off[n], e1 = d.edg_off[n + 1];
+            const int cnt = e1 - e0;
+            if (cnt > TE || nb1 - nb0 < 1 || d.nbr[nb0].x != n) return false;
+            // triangulation check: {ring neighbours} == {other ends of the edges}, same depths
+            a.clear();
+            b.clear();
+            for (int k = nb0 + 1; k < nb1; ++k) a.emplace_back(d.nbr[k].x, d.nbr[k].y);
+            for (int k = e0; k < e1; ++k) {
+                if (d.edg[k].y == n) return false;
+                b.emplace_back(d.edg[k].y, FCT_META_DEPTH(d.edg[k].z));
+            }
+            std::sort(a.begin(), a.end());
+            std::sort(b.begin(), b.end());
+            if (a != b) return false;
+            for (size_t k = 1; k < b.size(); ++k)
+                if (b[k].first == b[k - 1].first) return false;
+            out.hdr.push_back(make_int4(n, std::max(nlev_n[n] - 1, 0), d.fillmin[n], (d.nbr[nb0].y & 0xffff) | (cnt << 16)));
+            out.work_off.push_back(tile_wo[i]);
+            for (int k = 0; k < TE; ++k) {
+                if (k >= cnt) {
+                    out.ent.push_back(make_int4(0, 0, 0, 0));
+                    continue;
+                }
+                const int4 e = d.edg[e0 + k];
+                const int m = e.y;
+                if (stamp[m] != tile) {
+                    stamp[m] = tile;
+                    local[m] = nrows++;
+                    out.rows.push_back(make_int2(m, std::max(nlev_n[m] - 1, 0)));
+                }
+                out.ent.push_back(make_int4(e.x, local[m], e.z, m));
+            }
+        }
+        out.work_off.push_back(items);
+        out.max_rows = std::max(out.max_rows, nrows);
+        out.row_off.push_back((int)out.rows.size());
+        ++tile;
+    }
+    out.ntiles = tile;
+    return true;
+}
+
 }   // namespace fct

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "fct_kernels.cuh"
+#include "fct_tile_kernels.cuh"
 
 namespace fct {
 
@@ -23,6 +24,23 @@ bool build_derived(int N, int H, int E, int G, int nl, const int *nlev_e, const 
                    const int *nie_num, const int *nie, int nie_dim, const int *edges,
                    const int *edge_tri, DerivedHost &out);
 
+// Per-tile tables of the tile-staged kernels (see fct_tile_kernels.cuh), for one node list.
+struct TileSetHost {
+    std::vector<int> row_off;
+    std::vector<int2> rows;
+    std::vector<int4> hdr;
+    std::vector<int> work_off;
+    std::vector<int4> ent;
+    int ntiles = 0, max_rows = 0;
+};
+// Greedy tiling of `list` (nullptr: the identity 0..N-1): a tile closes after TN nodes or when its
+// work items (slots of `vec` levels, padded so a node never straddles a block iteration of
+// `threads` items) would exceed `budget`.  Returns false when the mesh is not a triangulation in
+// the sense the merged gather list needs (ring neighbours == edge neighbours with equal depths) or
+// a node has more than TE edges: the caller then keeps the general (untiled) kernels.
+bool build_tileset(const DerivedHost &d, const int *nlev_n, int N, int NT, const std::vector<int> *list,
+                   int TN, int TE, int vec, int threads, int budget, TileSetHost &out);
+
 struct Plan {
     unsigned magic = 0x504c414eu;
     int N = 0, H = 0, E = 0, G = 0, nl = 0, nie_dim = 0;
@@ -31,6 +49,9 @@ struct Plan {
     MeshDev dev{};          // device pointers
     int *d_boundary = nullptr, *d_interior = nullptr;
     int n_boundary = 0, n_interior = 0;
+    // tile-staged fused kernels: [phase A / B][0 all owned nodes, 1 boundary list, 2 interior list]
+    TileDev tiles[2][3] = {};
+    bool tiles_ok = false;
     std::vector<void *> owned;   // device allocations to free
 };
 

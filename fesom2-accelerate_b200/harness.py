@@ -264,7 +264,7 @@ class DeviceFields:
                 names.append("UV_rhs")
         for k in names:
             self.download_field(k, getattr(out, k), tracer)
-        self.download_field("fct_adf_h_out" if mode == 1 else "fct_adf_h", out.fct_adf_h, tracer)
+        self.download_field("fct_adf_h_out" if mode >= 1 else "fct_adf_h", out.fct_adf_h, tracer)
         self.stream.sync()
         return out
 

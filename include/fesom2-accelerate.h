@@ -160,6 +160,10 @@ void free_pinned_doubles_(void **hostptr, int *istat);
 void free_stream_(void **stream, int *istat);
 /* 0: one kernel per reference stage (default, materialises UV_rhs); 1: fused phase kernels */
 void fct_ale_set_fused_(int *fused);
+/* tuning knob: same effect as the environment variable FCT_<name> (NUL-terminated name), e.g.
+ * "TILE" 0/1, "TILE_NODES", "TILE_ITERS" (read when a plan is created), "TILE_VARIANT_A",
+ * "TILE_VARIANT_B", "TILE_AHEAD" (read at every launch).  Results never depend on them. */
+void fct_ale_tune_(const char *name, int *value);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 void fct_ale_launch_count_(long long *count);
 /* name and compute capability of the bound device; istat=1 when there is none */
@@ -208,16 +212,19 @@ void fct_ale_field_download_(void **fields, int *field, int *tracer, real_type *
                              int *istat);
 
 /* One fct_ale step a1..c over all tracers of `fields`, everything resident on the device.
- *   *mode 0: ten stage kernels (one per reference kernel);  *mode 1: two fused phase kernels.
+ *   *mode 0: ten stage kernels (one per reference kernel);  *mode 1: two fused phase kernels,
+ *   tile-staged through shared memory when the plan's tiles fit;  *mode 2: the fused kernels
+ *   without tile staging (measured alternative).
  * When `halo` is non-null the fct_plus / fct_minus halo exchange runs between b2 and b3
  * horizontal over NVLink, overlapped with the interior nodes' phase B work.
- * The limited horizontal fluxes are written to the FCT_ADF_H_OUT buffer in mode 1 (the in-place
+ * The limited horizontal fluxes are written to the FCT_ADF_H_OUT buffer in modes 1 and 2 (the in-place
  * update of the reference would race between the two end nodes of an edge) and in place
  * (FCT_ADF_H) in mode 0.  *alg_state = 10 on success. */
 void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_type *dt,
                    real_type *flux_eps, real_type *bignumber, int *alg_state);
 /* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,
- * 6 b3v, 7 b3h, 8 c_v, 9 c_h; 10 fused phase A, 11 fused phase B */
+ * 6 b3v, 7 b3h, 8 c_v, 9 c_h; 10 fused phase A, 11 fused phase B; 12 / 13 the tile-staged
+ * fused phases */
 void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, real_type *flux_eps,
                     real_type *bignumber, int *istat);
 

@@ -223,8 +223,11 @@ void oracle_b3_horizontal(int n_edges, int nl, const int *nlev_elem, const int *
     }
 }
 
-/* c vertical: docs/refactoring.md:295-300 (Fortran grouping (x*dt)/area); numpy twin
- * kernels/fct_ale_c_vertical.py:41-44 groups x*(dt/area) -> agreement to 1e-12 relative only */
+/* c vertical: docs/refactoring.md:295-300.  The flux term is grouped x * (dt / area) exactly like
+ * both executable statements of this stage in the reference -- kernels/fct_ale_c_vertical.cu:12
+ * and the numpy twin kernels/fct_ale_c_vertical.py:41-44 -- so the golden vectors of the twin
+ * are reproduced bit for bit.  The Fortran listing writes x*dt/area = (x*dt)/area, which differs
+ * from this by at most a few ulp (well inside the 1e-12 relative bar of BASELINE.json). */
 void oracle_c_vertical(int n_nodes, const int *nlev_nod, int nl, double *del_v, const double *ttf,
                        const double *hnode, const double *lo, const double *hnode_new,
                        const double *adf_v, const double *area, double dt)
@@ -235,13 +238,14 @@ void oracle_c_vertical(int n_nodes, const int *nlev_nod, int nl, double *del_v, 
         const int nz = nlev_nod[n] - 1;
         for (int z = 0; z < nz; ++z) {
             const size_t i = n * L + z;
-            del_v[i] = del_v[i] - ttf[i] * hnode[i] + lo[i] * hnode_new[i]
-                       + (v[z] - v[z + 1]) * dt / ar[z];
+            del_v[i] = del_v[i] - (ttf[i] * hnode[i]) + (lo[i] * hnode_new[i])
+                       + ((v[z] - v[z + 1]) * (dt / ar[z]));
         }
     }
 }
 
-/* c horizontal: docs/refactoring.md:303-314; numpy twin kernels/fct_ale_c_horizontal.py:53-71 */
+/* c horizontal: docs/refactoring.md:303-314; grouping h * (dt / area) as in
+ * kernels/fct_ale_c_horizontal.cu:25-26 and the numpy twin kernels/fct_ale_c_horizontal.py:53-71 */
 void oracle_c_horizontal(int n_edges, int nl, const int *nlev_elem, const int *edges,
                          const int *edge_tri, const double *adf_h, const double *area, double *del_h,
                          double dt)
@@ -252,8 +256,8 @@ void oracle_c_horizontal(int n_edges, int nl, const int *nlev_elem, const int *e
         const double *h = adf_h + (size_t)g * L;
         const int nz = edge_depth(edge_tri, nlev_elem, g);
         for (int z = 0; z < nz; ++z) {
-            del_h[n1 * L + z] = del_h[n1 * L + z] + h[z] * dt / area[n1 * nl + z];
-            del_h[n2 * L + z] = del_h[n2 * L + z] - h[z] * dt / area[n2 * nl + z];
+            del_h[n1 * L + z] = del_h[n1 * L + z] + (h[z] * (dt / area[n1 * nl + z]));
+            del_h[n2 * L + z] = del_h[n2 * L + z] - (h[z] * (dt / area[n2 * nl + z]));
         }
     }
 }

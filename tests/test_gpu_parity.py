@@ -57,7 +57,7 @@ def test_handle_abi_chain(mesh_mod, harness, abi, oracle_mod, name, fused):
 
 
 @pytest.mark.parametrize("name", ["tiny", "pi", "core2", "adversarial", "adversarial_even"])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
     m, f = cases(mesh_mod, name)
     want = f.copy()
@@ -175,10 +175,11 @@ def test_step_is_repeatable_and_deterministic(mesh_mod, harness):
 
 
 @pytest.mark.parametrize("nparts", [2, 5])
-def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled):
     """Every partition of a mesh run on this GPU with the halo exchange emulated through the host:
     owned results of all partitions must reproduce the single-domain oracle bit for bit (boundary /
-    interior node lists, halo numbering, cut edges duplicated on both sides)."""
+    interior node lists and their tiles, halo numbering, cut edges duplicated on both sides)."""
     m, f = cases(mesh_mod, "pi")
     want = f.copy()
     oracle_mod.fct_ale(m, want)
@@ -186,9 +187,12 @@ def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts):
     plans = [harness.DevicePlan(p.mesh) for p in parts]
     lfs = [mesh_mod.slice_fields(f, p) for p in parts]
     dfs = [harness.DeviceFields(pl, 1, with_uv=False) for pl in plans]
+    stA = ["phaseA_tile_boundary", "phaseA_tile_interior"] if tiled else ["phaseA"]
+    stB = ["phaseB_tile_interior", "phaseB_tile_boundary"] if tiled else ["phaseB"]
     for df, lf in zip(dfs, lfs):
         df.upload(lf)
-        df.stage("phaseA", lf)
+        for s in stA:
+            df.stage(s, lf)
     # exchange_nod(fct_plus, fct_minus) through the host
     gplus = np.empty_like(f.fct_plus)
     gminus = np.empty_like(f.fct_minus)
@@ -201,7 +205,8 @@ def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts):
         df.upload_field("fct_plus", np.ascontiguousarray(gplus[p.mesh.node_gid]))
         df.upload_field("fct_minus", np.ascontiguousarray(gminus[p.mesh.node_gid]))
         df.stream.sync()
-        df.stage("phaseB", lf)
+        for s in stB:
+            df.stage(s, lf)
     got = f.copy()
     for p, df, lf in zip(parts, dfs, lfs):
         n = p.mesh.myDim_nod2D

@@ -34,10 +34,14 @@ def run(nx, ny, nl, T=1, reps=10, label=""):
         tot += ms
         print(f"   stage {s:4s} {ms*1e3:9.1f} us")
     print(f"   staged sum {tot*1e3:9.1f} us -> {Sn*T/tot/1e6:8.2f} G upd/s, alg {balg/tot/1e6:8.1f} GB/s")
-    for s in ["phaseA", "phaseB"]:
+    Sg8 = 8 * Sg * T
+    Sn8 = 8 * Sn * T
+    algA, algB = 8 * Sn8 + Sg8 + 16 * m.myDim_nod2D * T, 13 * Sn8 + 2 * Sg8
+    for s in ["phaseA", "phaseB", "phaseA_tile", "phaseB_tile"]:
         ms = timeit(lambda: df.stage(s, f, sync=False))
-        print(f"   fused {s} {ms*1e3:9.1f} us")
-    for mode in (0, 1):
+        alg = algA if "A" in s else algB
+        print(f"   fused {s:12s} {ms*1e3:9.1f} us   alg {alg/ms/1e6:8.1f} GB/s = {alg/ms/1e6/6547.2*100:5.1f}%")
+    for mode in (0, 2, 1):
         ms = timeit(lambda: df.step(f, mode=mode, sync=False))
         print(f"   step mode {mode}: {ms*1e3:9.1f} us -> {Sn*T/ms/1e6:8.2f} G upd/s, alg {balg/ms/1e6:8.1f} GB/s = {balg/ms/1e6/6547.2*100:5.1f}% of 6547 GB/s")
     df.free(); plan.free()
