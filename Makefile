@@ -18,7 +18,7 @@ $(OUT)/%.o: $(SRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(PTXAS) -c $< -o $@
 
 $(OUT)/libfesom2-accelerate.so: $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lnccl
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl
 
 oracle:
 	$(MAKE) -C oracle

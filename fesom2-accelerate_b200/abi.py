@@ -62,7 +62,7 @@ def load() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             raise AbiError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()) first; "
                            "there is no CPU fallback")
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(LIB_PATH)
     return _lib
 
 

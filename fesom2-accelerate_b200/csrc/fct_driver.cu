@@ -275,11 +275,11 @@ struct TileVariant {
     const char *name;
 };
 static const TileVariant g_variants_a[] = {
-    {k_phaseA_tile<2, 8, 3>, "hb8-min3"}, {k_phaseA_tile<2, 0, 4>, "hb0-min4"}, {k_phaseA_tile<2, 4, 3>, "hb4-min3"},
+    {k_phaseA_tile<2, 0, 4>, "hb0-min4"}, {k_phaseA_tile<2, 8, 3>, "hb8-min3"}, {k_phaseA_tile<2, 4, 3>, "hb4-min3"},
     {k_phaseA_tile<2, 8, 2>, "hb8-min2"}, {k_phaseA_tile<2, 0, 3>, "hb0-min3"}, {k_phaseA_tile<2, 6, 4>, "hb6-min4"},
 };
 static const TileVariant g_variants_b[] = {
-    {k_phaseB_tile<2, 8, 2>, "hb8-min2"}, {k_phaseB_tile<2, 0, 3>, "hb0-min3"}, {k_phaseB_tile<2, 4, 3>, "hb4-min3"},
+    {k_phaseB_tile<2, 4, 3>, "hb4-min3"}, {k_phaseB_tile<2, 0, 3>, "hb0-min3"}, {k_phaseB_tile<2, 8, 2>, "hb8-min2"},
     {k_phaseB_tile<2, 8, 3>, "hb8-min3"}, {k_phaseB_tile<2, 4, 2>, "hb4-min2"}, {k_phaseB_tile<2, 6, 3>, "hb6-min3"},
 };
 

@@ -4,6 +4,7 @@
 // grouped ncclSend / ncclRecv move them over NVLink, and the receives land directly in the halo
 // rows (halo nodes are numbered grouped by owner, so no unpack is needed).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstdio>
@@ -28,6 +29,59 @@ struct Halo {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
 };
+
+// NCCL is bound at first use, not at link time: a host process that already carries an NCCL (for
+// instance torch's bundled one, same SONAME as the system library) keeps a single copy, and the
+// library loads on machines without NCCL as long as no halo is created.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi load_nccl()
+{
+    NcclApi a;
+    void *h = nullptr;
+    auto sym = [&](const char *name) -> void * {
+        void *p = dlsym(RTLD_DEFAULT, name);
+        if (!p) {
+            if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+            if (h) p = dlsym(h, name);
+        }
+        return p;
+    };
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+    a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+    a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv &&
+           a.GetErrorString;
+    if (!a.ok) std::fprintf(stderr, "fesom2-accelerate: NCCL (libnccl.so.2) is not available: no multi-GPU halo exchange\n");
+    return a;
+}
+static const NcclApi &nccl()
+{
+    static const NcclApi a = load_nccl();
+    return a;
+}
+#define ncclGetUniqueId nccl().GetUniqueId
+#define ncclCommInitRank nccl().CommInitRank
+#define ncclCommDestroy nccl().CommDestroy
+#define ncclGroupStart nccl().GroupStart
+#define ncclGroupEnd nccl().GroupEnd
+#define ncclSend nccl().Send
+#define ncclRecv nccl().Recv
+#define ncclGetErrorString nccl().GetErrorString
 
 bool halo_valid(Halo *h) { return h && h->magic == HALO_MAGIC; }
 cudaStream_t halo_comm_stream(Halo *h) { return h->comm_stream; }
@@ -112,6 +166,8 @@ void fct_ale_comm_unique_id_(char *id128, int *istat)
 {
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    *istat = 1;
+    if (!nccl().ok) return;
     *istat = nccl_ok(ncclGetUniqueId(&id), "ncclGetUniqueId") ? 0 : 1;
     if (*istat == 0) std::memcpy(id128, &id, 128);
 }
@@ -123,7 +179,7 @@ void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int 
     *halo = nullptr;
     *istat = 1;
     Plan *p = plan ? static_cast<Plan *>(*plan) : nullptr;
-    if (!p || p->magic != PLAN_MAGIC) return;
+    if (!p || p->magic != PLAN_MAGIC || !nccl().ok) return;
     Halo *h = new (std::nothrow) Halo;
     if (!h) return;
     h->plan = p;

@@ -387,19 +387,21 @@ def partition_mesh(mesh: Mesh, nparts: int, ranks: Optional[List[int]] = None) -
     parts = []
     halo_gids = {}
     wanted = range(nparts) if ranks is None else ranks
-    # halo sets of every rank are needed to build the send lists of the wanted ranks
     tri_owner = owner[tri]
-    for r in range(nparts):
-        emask = (tri_owner == r).any(1)
-        nodes_r = np.unique(tri[emask].ravel())
-        hg = nodes_r[owner[nodes_r] != r]
-        # grouped by owner, ascending gid inside a group
-        hg = hg[np.lexsort((hg, owner[hg]))]
-        halo_gids[r] = hg
+
+    def halo_of(r):
+        """halo nodes of rank r, grouped by owner, ascending gid inside a group (cached)."""
+        if r not in halo_gids:
+            emask = (tri_owner == r).any(1)
+            nodes_r = np.unique(tri[emask].ravel())
+            hg = nodes_r[owner[nodes_r] != r]
+            halo_gids[r] = hg[np.lexsort((hg, owner[hg]))]
+        return halo_gids[r]
+
     for r in wanted:
         lo, hi = int(bounds[r]), int(bounds[r + 1])
         n_own = hi - lo
-        hg = halo_gids[r]
+        hg = halo_of(r)
         H = hg.size
         gids = np.concatenate([np.arange(lo, hi), hg])
         loc = np.full(N, -1, dtype=np.int64)
@@ -435,10 +437,10 @@ def partition_mesh(mesh: Mesh, nparts: int, ranks: Optional[List[int]] = None) -
             idx = np.flatnonzero(own_h == p)
             recv[int(p)] = (int(n_own + idx[0]), int(idx.size))
         send = {}
-        for p in range(nparts):
-            if p == r:
-                continue
-            hp = halo_gids[p]
+        # node adjacency is symmetric: the ranks holding my nodes in their halo are the owners of
+        # my halo nodes
+        for p in [int(q) for q in np.unique(own_h)]:
+            hp = halo_of(p)
             mine = hp[owner[hp] == r]
             if mine.size:
                 send[int(p)] = (mine - lo).astype(np.int32)
@@ -468,3 +470,44 @@ def slice_fields(f: Fields, part: Partition) -> Fields:
         else:
             kw[k] = v[g].copy()
     return Fields(**kw)
+
+
+def fast_fields(mesh: Mesh, seed: int = 1, alloc=None, with_uv: bool = False) -> Fields:
+    """Benchmark-sized synthetic fields in seconds rather than minutes: every array is filled by
+    tiling one random block (different phase and affine map per array).  Same value ranges as
+    make_fields; no poisoning and no zeroing below the sea floor (those cells are never used).
+    `alloc(shape)` lets the caller place the arrays in page-locked memory."""
+    rng = np.random.default_rng(seed)
+    alloc = alloc or (lambda shape: np.empty(shape, dtype=np.float64))
+    B = 1 << 22
+    base = rng.standard_normal(B + 4096)
+    NT, L, nl, G = mesh.nnod, mesh.L, mesh.nl, mesh.myDim_edge2D
+
+    def fill(shape, scale, offset, phase, clip=None):
+        a = alloc(shape)
+        flat = a.reshape(-1)
+        blk = base[phase: phase + B] * scale + offset
+        if clip is not None:
+            np.clip(blk, clip[0], clip[1], out=blk)
+        for i in range(0, flat.size, B):
+            n = min(B, flat.size - i)
+            flat[i:i + n] = blk[:n]
+        return a
+
+    ttf = fill((NT, L), 0.1, 10.0, 0)
+    lo = fill((NT, L), 0.1, 10.0, 0)
+    lo += fill((NT, L), 0.01, 0.0, 17)
+    area = fill((NT, nl), 0.25, 1.5, 101, clip=(1.0, 2.0))
+    area_inv = alloc((NT, nl))
+    np.divide(1.0, area, out=area_inv)
+    hnode = fill((NT, L), 10.0, 27.0, 211, clip=(5.0, 50.0))
+    hnode_new = fill((NT, L), 10.0, 27.0, 211, clip=(5.0, 50.0))
+    hnode_new *= 1.0 + 1e-3 * base[307]
+    f = Fields(
+        ttf=ttf, fct_LO=lo, fct_adf_v=fill((NT, nl), 1.0, 0.0, 401), fct_adf_h=fill((G, L), 1.0, 0.0, 503),
+        area=area, area_inv=area_inv, hnode=hnode, hnode_new=hnode_new,
+        del_ttf_advvert=fill((NT, L), 1.0, 0.0, 601), del_ttf_advhoriz=fill((NT, L), 1.0, 0.0, 701),
+        fct_ttf_max=fill((NT, L), 0.0, SENTINEL, 0), fct_ttf_min=fill((NT, L), 0.0, SENTINEL, 0),
+        fct_plus=fill((NT, L), 0.0, SENTINEL, 0), fct_minus=fill((NT, L), 0.0, SENTINEL, 0),
+        UV_rhs=fill((mesh.myDim_elem2D, L, 2), 0.0, SENTINEL, 0) if with_uv else None)
+    return f

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fesom2-accelerate.h declares; the
+product never links the oracle; without a GPU the compute entry points fail loudly."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "fesom2-accelerate.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\bvoid\s+(\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(abi):
+    hs = header_symbols()
+    assert sorted(abi.SYMBOLS) == hs, set(abi.SYMBOLS) ^ set(hs)
+
+
+def test_library_exports_every_symbol(abi):
+    lib = abi.load()
+    for s in abi.SYMBOLS:
+        assert hasattr(lib, s), s
+    out = subprocess.run(["nm", "-D", "--defined-only", abi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(abi.SYMBOLS) <= exported
+    # the reference's 18 C symbols + its CPU-oracle names
+    for s in ("set_mpi_rank_", "transfer_mesh_", "alloc_var_", "reserve_var_", "allocate_pinned_doubles_",
+              "transfer_var_", "transfer_var_async_", "make_stream_", "await_stream_",
+              "fct_ale_pre_comm_acc_", "fct_ale_inter_comm_acc_", "fct_ale_post_comm_acc_",
+              "fct_ale_a1_accelerated", "fct_ale_a2_accelerated", "fct_ale_a1_a2_accelerated",
+              "fct_ale_a1_reference_", "fct_ale_a2_reference_", "fct_ale_a3_reference_", "fct_ale_a4_reference_",
+              "fct_ale_pre_comm_"):
+        assert s in exported, s
+
+
+def test_product_does_not_depend_on_the_oracle(abi):
+    out = subprocess.run(["ldd", abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libref" not in out
+    pkg_dir = os.path.dirname(abi.LIB_PATH.replace("/lib/", "/"))
+    for root, _, files in os.walk(os.path.join(ROOT, "fesom2-accelerate_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "libfct_oracle" not in txt and "libref" not in txt, f
+
+
+def test_gpumemory_struct_prefix_matches_reference(abi):
+    """Leading members of struct gpuMemory = the reference's (include/fesom2-accelerate.h:19-28)."""
+    g = abi.GpuMemory
+    assert [f[0] for f in g._fields_[:4]] == ["host_pointer", "device_pointer", "size", "event"]
+    assert g.host_pointer.offset == 0 and g.device_pointer.offset == 8 and g.size.offset == 16 and g.event.offset == 24
+
+
+def test_no_cpu_fallback_without_a_device(abi, harness, mesh_mod):
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(abi.AbiError):
+        abi.device_info()
+    m = mesh_mod.make_workload("tiny")
+    with pytest.raises(abi.AbiError):
+        harness.DevicePlan(m)
+    with pytest.raises(abi.AbiError):
+        harness.HandleChain(m, mesh_mod.make_fields(m))

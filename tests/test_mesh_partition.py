@@ -1,0 +1,119 @@
+"""CPU: synthetic mesh invariants, partitions, and the N>1 path of the host logic:
+partitioned oracle runs (in-process and over a world_size-2 gloo group) must reproduce the
+single-domain oracle bit for bit."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits_equal
+
+OUT_KEYS = ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "fct_adf_h",
+            "del_ttf_advvert", "del_ttf_advhoriz")
+
+
+def test_mesh_invariants(mesh_mod):
+    m = mesh_mod.make_workload("pi")
+    N, E, G = m.myDim_nod2D, m.myDim_elem2D, m.myDim_edge2D
+    assert 2900 < N < 3200 and 5600 < E < 6100          # BASELINE.json config 0 (3,140 nodes, ~5.8k elements)
+    tri = m.elem2D_nodes - 1
+    assert tri.min() == 0 and tri.max() == N - 1
+    # Euler characteristic of a planar triangulation with holes: V - E + F = 1 - holes <= 1
+    assert N - G + E <= 1
+    # node depth = max over its ring (the invariant the model guarantees)
+    want = np.zeros(N, dtype=np.int32)
+    np.maximum.at(want, tri.ravel(), np.repeat(m.nlevels_elem, 3))
+    assert np.array_equal(want, m.nlevels_nod2D)
+    # every edge: left element present, both elements contain both nodes
+    e = m.edges - 1
+    et = m.edge_tri - 1
+    assert (et[:, 0] >= 0).all()
+    for side in (0, 1):
+        ok = et[:, side] >= 0
+        t = tri[et[ok, side]]
+        assert ((t == e[ok, 0:1]).any(1) & (t == e[ok, 1:2]).any(1)).all()
+    assert (m.edge_tri[:, 1] == 0).sum() > 0             # the land mask produced boundary edges
+    # ring table consistent with the element table
+    for n in (0, N // 2, N - 1):
+        ring = m.nod_in_elem2D[n, : m.nod_in_elem2D_num[n]] - 1
+        assert sorted(ring) == sorted(np.flatnonzero((tri == n).any(1)))
+    assert abs(m.bytes_alg() / m.S_n() - 240) < 8        # ~240 B per update
+
+
+def test_hilbert_locality(mesh_mod):
+    m = mesh_mod.make_workload("core2")
+    e = m.edges.astype(np.int64) - 1
+    assert np.median(np.abs(e[:, 0] - e[:, 1])) < 64     # neighbours stay close in memory
+
+
+def _run_partitioned(mesh_mod, oracle, m, f, nparts, exchange):
+    parts = mesh_mod.partition_mesh(m, nparts)
+    lfs = [mesh_mod.slice_fields(f, p) for p in parts]
+    for p, lf in zip(parts, lfs):
+        oracle.pre_comm(p.mesh, lf)
+    exchange(parts, lfs)
+    got = f.copy()
+    for p, lf in zip(parts, lfs):
+        oracle.post_comm(p.mesh, lf)
+        n = p.mesh.myDim_nod2D
+        for k in OUT_KEYS:
+            if k == "fct_adf_h":
+                got.fct_adf_h[p.mesh.edge_gid] = lf.fct_adf_h
+            else:
+                getattr(got, k)[p.mesh.node_gid[:n]] = getattr(lf, k)[:n]
+    return got, parts
+
+
+def _host_exchange(parts, lfs):
+    """exchange_nod(fct_plus, fct_minus): send lists -> the receivers' halo ranges."""
+    for p, lf in zip(parts, lfs):
+        for peer, nodes in p.send_lists.items():
+            first, cnt = parts[peer].recv_ranges[p.rank]
+            assert cnt == nodes.size
+            lfs[peer].fct_plus[first:first + cnt] = lf.fct_plus[nodes]
+            lfs[peer].fct_minus[first:first + cnt] = lf.fct_minus[nodes]
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 8])
+def test_partitioned_oracle_equals_single_domain(mesh_mod, oracle_mod, nparts):
+    m = mesh_mod.make_workload("pi")
+    f = mesh_mod.make_fields(m)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    got, parts = _run_partitioned(mesh_mod, oracle_mod, m, f, nparts, _host_exchange)
+    for k in OUT_KEYS:
+        assert bits_equal(getattr(got, k), getattr(want, k)), k
+    # partition bookkeeping
+    assert sum(p.mesh.myDim_nod2D for p in parts) == m.myDim_nod2D
+    for p in parts:
+        n = p.mesh.myDim_nod2D
+        assert p.boundary_nodes.size + p.interior_nodes.size == n
+        assert set(p.send_lists) == set(p.recv_ranges)
+        sent = np.unique(np.concatenate(list(p.send_lists.values()))) if p.send_lists else np.empty(0)
+        assert np.array_equal(sent, p.boundary_nodes)       # send set == nodes with a halo neighbour
+        w = (p.mesh.nlevels_nod2D[:n].astype(np.int64) - 1).sum()
+        assert abs(w - m.S_n() / nparts) < 0.15 * m.S_n() / nparts   # balanced on node-levels
+
+
+def test_lazy_partition_matches_full(mesh_mod):
+    m = mesh_mod.make_workload("pi")
+    full = mesh_mod.partition_mesh(m, 5)
+    one = mesh_mod.partition_mesh(m, 5, ranks=[3])[0]
+    ref = full[3]
+    assert np.array_equal(one.mesh.node_gid, ref.mesh.node_gid)
+    assert np.array_equal(one.mesh.edges, ref.mesh.edges)
+    assert one.recv_ranges == ref.recv_ranges
+    assert all(np.array_equal(one.send_lists[k], ref.send_lists[k]) for k in ref.send_lists)
+
+
+def test_world_size_2_gloo(tmp_path):
+    """Two processes, one partition each, halo exchange over torch.distributed (gloo, CPU)."""
+    script = os.path.join(ROOT, "tests", "gloo_worker.py")
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), script, str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
