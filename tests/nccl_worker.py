@@ -1,0 +1,67 @@
+"""Worker of tests/test_gpu_multi.py: one rank per GPU, partition r of a mesh on GPU r, the fused
+step with the NVLink halo exchange (NCCL) inside, owned results checked against the single-domain
+oracle bit for bit.  Modes: 1 = tile-staged overlapped schedule, 2 = untiled, 0 = staged."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch.distributed as dist  # noqa: E402  (before the product library: one NCCL per process)
+
+import oracle  # noqa: E402
+
+mesh_mod = importlib.import_module("fesom2-accelerate_b200.mesh")
+harness = importlib.import_module("fesom2-accelerate_b200.harness")
+abi = importlib.import_module("fesom2-accelerate_b200.abi")
+comm = importlib.import_module("fesom2-accelerate_b200.hostcomm")
+
+KEYS = ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "del_ttf_advvert", "del_ttf_advhoriz")
+
+
+def main():
+    out, name = sys.argv[1], sys.argv[2]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    abi.load().set_mpi_rank_(abi.ci(int(os.environ.get("LOCAL_RANK", rank))), abi.ci(world))
+    m = mesh_mod.make_workload(name)
+    T = 2
+    fs = [mesh_mod.make_fields(m, seed=1 + t) for t in range(T)]
+    for k in ("area", "area_inv", "hnode", "hnode_new"):
+        setattr(fs[1], k, getattr(fs[0], k))
+    wants = []
+    for f in fs:
+        w = f.copy()
+        oracle.fct_ale(m, w)
+        wants.append(w)
+    part = mesh_mod.partition_mesh(m, world, ranks=[rank])[0]
+    plan = harness.DevicePlan(part.mesh)
+    uid = comm.broadcast_bytes(harness.HaloLink.unique_id() if rank == 0 else None)
+    halo = harness.HaloLink(plan, part, uid)
+    n = part.mesh.myDim_nod2D
+    g = part.mesh.node_gid[:n]
+    for mode in (1, 2, 0):
+        df = harness.DeviceFields(plan, T, with_uv=True)
+        lfs = [mesh_mod.slice_fields(f, part) for f in fs]
+        for t in range(T):
+            df.upload(lfs[t], tracer=t, static=(t == 0))
+        for rep in range(1):
+            st = df.step(lfs[0], mode=mode, halo=halo)
+            assert st == 10, (mode, st)
+        for t in range(T):
+            got = df.download(lfs[t], tracer=t, mode=mode)
+            for k in KEYS:
+                assert np.array_equal(getattr(got, k)[:n], getattr(wants[t], k)[g]), (rank, mode, t, k)
+            assert np.array_equal(got.fct_adf_h, wants[t].fct_adf_h[part.mesh.edge_gid]), (rank, mode, t, "fct_adf_h")
+        df.free()
+    dist.barrier()
+    halo.free()
+    plan.free()
+    open(os.path.join(out, f"ok_{rank}"), "w").close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
