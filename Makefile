@@ -9,7 +9,7 @@ PKG      = fesom2-accelerate_b200
 SRC      = $(PKG)/csrc
 OUT      = $(PKG)/lib
 OBJS     = $(OUT)/fct_driver.o $(OUT)/fct_fields.o $(OUT)/fct_halo.o $(OUT)/fct_plan.o
-HDRS     = $(SRC)/fct_kernels.cuh $(SRC)/fct_tile_kernels.cuh $(SRC)/fct_plan.h $(SRC)/fct_internal.h include/fesom2-accelerate.h
+HDRS     = $(SRC)/fct_kernels.cuh $(SRC)/fct_tile_kernels.cuh $(SRC)/fct_warp_kernels.cuh $(SRC)/fct_plan.h $(SRC)/fct_internal.h include/fesom2-accelerate.h
 
 all: $(OUT)/libfesom2-accelerate.so oracle
 

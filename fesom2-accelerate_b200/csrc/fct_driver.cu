@@ -266,6 +266,103 @@ static void build_plan_tiles(Plan *p, const DerivedHost &d, const int *nlev_n)
     p->tiles_ok = true;
 }
 
+// ---- warp-item kernels: plan tables, launch ---------------------------------------------------
+static const int WT_SMEM_MAX = 227 * 1024;
+
+static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
+{
+    p->wtiles_ok = false;
+    if (env_int("FCT_WTILE", 1) == 0) return;
+    const int verbose = env_int("FCT_VERBOSE", 0);
+    const int slots = (p->nl - 1 + 1) / 2;   // level pairs of the deepest possible column
+    int nch = env_int("FCT_WT_NCH", 0);
+    if (nch <= 0) nch = slots > 32 ? 2 : 1;
+    if (nch > 2 || slots > 32 * nch) {
+        if (verbose) std::fprintf(stderr, "fesom2-accelerate: nl = %d does not fit a warp item: no warp-item tiles\n", p->nl);
+        return;
+    }
+    // default footprint: three CTAs per SM up to 48 levels, two beyond
+    const int cap_dflt = (p->nl <= 48 ? 74 : 112) * 1024;
+    int cap = env_int("FCT_WT_SMEM", 0);   // 0: default
+    cap = cap <= 0 ? cap_dflt : std::min(std::max(cap, 8 * 1024), WT_SMEM_MAX);
+    int TN = env_int("FCT_WT_NODES", 0);
+    TN = TN <= 0 ? 64 : std::min(TN, 255);
+    const std::vector<int> *lists[3] = {nullptr, &d.boundary, &d.interior};
+    const int nsets = p->H > 0 ? 3 : 1;
+    WarpTilesHost h[3];
+    for (int s = 0; s < nsets; ++s) {
+        if (!build_warptiles(d, nlev_n, p->N, p->N + p->H, p->G, p->pitch, lists[s], TN, nch, cap, h[s])) {
+            if (verbose) std::fprintf(stderr, "fesom2-accelerate: mesh is not eligible for the warp-item kernels\n");
+            return;
+        }
+    }
+    for (int s = 0; s < nsets; ++s) {
+        WarpTilesDev &T = p->wtiles[s];
+        T.blob = upload_vec(p, h[s].blob);
+        T.blob_off = upload_vec(p, h[s].blob_off);
+        T.ntiles = h[s].ntiles;
+        T.smem_bytes = h[s].smem_bytes;
+        if (!T.blob || !T.blob_off) return;
+        if (verbose && h[s].ntiles > 0)
+            std::fprintf(stderr,
+                         "fesom2-accelerate: warp tiles[%d]: %d tiles, %.1f nodes/tile, %.2f staged rows/node, %.2f staged edge rows/node "
+                         "(%.2f edge uses/node), lane fill %.1f%%, %.0f B plan/node, %d B smem, nch %d\n",
+                         s, h[s].ntiles, (double)h[s].nodes / h[s].ntiles, (double)h[s].staged_rows / h[s].nodes,
+                         (double)h[s].staged_erows / h[s].nodes, (double)h[s].edge_uses / h[s].nodes,
+                         100.0 * h[s].slots / std::max<long long>(h[s].lanes, 1), 16.0 * h[s].blob.size() / h[s].nodes,
+                         h[s].smem_bytes, nch);
+    }
+    p->wt_nch = nch;
+    p->wtiles_ok = true;
+}
+
+typedef void (*warp_kern_t)(Arrays, WarpTilesDev);
+struct WarpVariant {
+    warp_kern_t fn;
+    const char *name;
+};
+// [phase][nch - 1][minb - 1]
+static const WarpVariant g_wvariants[2][2][3] = {
+    {{{k_phaseA_warp<1, 1>, "A nch1 minb1"}, {k_phaseA_warp<1, 2>, "A nch1 minb2"}, {k_phaseA_warp<1, 3>, "A nch1 minb3"}},
+     {{k_phaseA_warp<2, 1>, "A nch2 minb1"}, {k_phaseA_warp<2, 2>, "A nch2 minb2"}, {k_phaseA_warp<2, 3>, "A nch2 minb3"}}},
+    {{{k_phaseB_warp<1, 1>, "B nch1 minb1"}, {k_phaseB_warp<1, 2>, "B nch1 minb2"}, {k_phaseB_warp<1, 3>, "B nch1 minb3"}},
+     {{k_phaseB_warp<2, 1>, "B nch2 minb1"}, {k_phaseB_warp<2, 2>, "B nch2 minb2"}, {k_phaseB_warp<2, 3>, "B nch2 minb3"}}},
+};
+
+// which: 0 all owned nodes, 1 boundary list, 2 interior list
+bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s)
+{
+    const bool isA = stage == ST_PHASE_A;
+    const WarpTilesDev &T = p->wtiles[which];
+    if (T.ntiles <= 0) return true;
+    if (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch) {
+        std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");
+        return false;
+    }
+    const int ph = isA ? 0 : 1, ni = p->wt_nch - 1;
+    const size_t smem = (size_t)T.smem_bytes;
+    // resident CTAs the register allocation is bounded for: as many as the shared memory admits
+    const int fit = (int)std::min<size_t>(3, std::max<size_t>(1, (size_t)(228 * 1024) / (smem + 1024)));
+    int minb = env_int(isA ? "FCT_WT_MINB_A" : "FCT_WT_MINB_B", 0);   // 0: default
+    minb = minb <= 0 ? fit : std::min(minb, 3);
+    const WarpVariant &v = g_wvariants[ph][ni][minb - 1];
+    static size_t attr_set[2][2][3] = {};
+    if (smem > attr_set[ph][ni][minb - 1]) {
+        if (!cuda_ok(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute"))
+            return false;
+        attr_set[ph][ni][minb - 1] = smem;
+        if (env_int("FCT_VERBOSE", 0)) {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, WT_THREADS, smem);
+            std::fprintf(stderr, "fesom2-accelerate: warp kernel %s: %zu B smem, %d CTAs/SM\n", v.name, smem, per_sm);
+        }
+    }
+    dim3 grid(T.ntiles, ntracers, 1);
+    v.fn<<<grid, WT_THREADS, smem, s>>>(A, T);
+    count_launch(1);
+    return cuda_ok(cudaGetLastError(), "warp kernel launch");
+}
+
 typedef void (*tile_kern_t)(Arrays, TileDev);
 
 // Variants of the tile kernels: HB edge-flux rows loaded ahead per item, MINB resident CTAs the
@@ -359,6 +456,7 @@ Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, co
         return nullptr;
     }
     build_plan_tiles(p, d, nlev_n);
+    build_plan_wtiles(p, d, nlev_n);
     return p;
 }
 
@@ -564,6 +662,7 @@ void fct_ale_pre_comm_acc_(int *alg_state, void **s, void **fct_ttf_max, void **
     A.ttf = dev<double>(ttf);
     A.lo = dev<double>(fct_LO);
     A.adf_v = dev<double>(fct_adf_v);
+    A.adf_v_out = A.adf_v;
     A.adf_h_in = dev<double>(fct_adf_h);
     A.adf_h_out = dev<double>(fct_adf_h);
     A.ttf_max = dev<double>(fct_ttf_max);
@@ -619,6 +718,7 @@ void fct_ale_inter_comm_acc_(int *alg_state, void **s, void **fct_plus, void **f
     cudaStream_t st = S(s);
     Arrays A = dense_arrays(*nl);
     A.adf_v = dev<double>(fct_adf_v);
+    A.adf_v_out = A.adf_v;
     A.plus = dev<double>(fct_plus);
     A.minus = dev<double>(fct_minus);
     MeshDev M;
@@ -919,6 +1019,7 @@ void fct_ale_c_acc_(int *alg_state, void **s, void **del_ttf_advvert, void **del
     A.ttf = dev<double>(ttf);
     A.lo = dev<double>(fct_LO);
     A.adf_v = dev<double>(fct_adf_v);
+    A.adf_v_out = A.adf_v;
     A.adf_h_in = dev<double>(fct_adf_h);
     A.adf_h_out = dev<double>(fct_adf_h);
     A.del_v = dev<double>(del_ttf_advvert);

@@ -21,7 +21,8 @@ struct FieldMeta {
 static FieldMeta meta_of(int id)
 {
     switch (id) {
-    case FCT_ADF_V: return {ROW_NODE, 0, true};
+    case FCT_ADF_V:
+    case FCT_ADF_V_OUT: return {ROW_NODE, 0, true};
     case FCT_AREA:
     case FCT_AREA_INV: return {ROW_NODE, 0, false};
     case FCT_HNODE:
@@ -60,6 +61,7 @@ static Arrays arrays_of(const Fields *f, int mode, double dt, double eps, double
     A.ttf = f->buf[FCT_TTF];
     A.lo = f->buf[FCT_LO];
     A.adf_v = f->buf[FCT_ADF_V];
+    A.adf_v_out = (mode >= 1) ? f->buf[FCT_ADF_V_OUT] : f->buf[FCT_ADF_V];
     A.adf_h_in = f->buf[FCT_ADF_H];
     A.adf_h_out = (mode >= 1) ? f->buf[FCT_ADF_H_OUT] : f->buf[FCT_ADF_H];
     A.ttf_max = f->buf[FCT_TTF_MAX];
@@ -218,6 +220,22 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     const Plan *p = f->plan;
     const int st = *stage;
     const Arrays A = arrays_of(f, st >= ST_PHASE_A ? 1 : 0, *dt, *flux_eps, *bignumber);
+    if (st >= ST_PHASE_A_WARP && st <= 23) {
+        // 18/19: all owned nodes; 20/21: phase A on the boundary / interior tiles; 22/23: phase B
+        if (!p->wtiles_ok) {
+            std::fprintf(stderr, "fesom2-accelerate: this plan has no warp-item tiles\n");
+            return;
+        }
+        const int which = st <= ST_PHASE_B_WARP ? 0 : 1 + ((st - 20) & 1);
+        const int phase = st <= ST_PHASE_B_WARP ? (st == ST_PHASE_A_WARP ? ST_PHASE_A : ST_PHASE_B)
+                                                : (st < 22 ? ST_PHASE_A : ST_PHASE_B);
+        if (which != 0 && p->H == 0) {
+            std::fprintf(stderr, "fesom2-accelerate: boundary / interior tiles exist on partitioned plans only\n");
+            return;
+        }
+        if (launch_warp(phase, A, p, which, f->T, S_(stream))) *istat = 0;
+        return;
+    }
     if (st >= ST_PHASE_A_TILE && st <= 17) {
         // 12/13: all owned nodes; 14/15: phase A on the boundary / interior list; 16/17: phase B
         if (!p->tiles_ok) {
@@ -279,9 +297,11 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
         }
         return;
     }
-    const bool tiled = p->tiles_ok && *mode == 1;
+    const bool warped = p->wtiles_ok && *mode == 1;
+    const bool tiled = p->tiles_ok && (*mode == 3 || (*mode == 1 && !warped));
     // one fused phase over a node set: 0 all owned, 1 boundary, 2 interior
     auto phase = [&](int stage, int which) -> bool {
+        if (warped) return launch_warp(stage, A, p, which, f->T, s);
         if (tiled) return launch_tile(stage, A, p, which, f->T, s);
         if (which == 0) return run_stage(f, A, stage, nullptr, 0, N, s);
         return which == 1 ? run_stage(f, A, stage, p->d_boundary, 0, p->n_boundary, s)

@@ -9,7 +9,8 @@ namespace fct {
 
 enum Stage {
     ST_A1 = 0, ST_A2 = 1, ST_A3 = 2, ST_B1V = 3, ST_B1H = 4, ST_B2 = 5, ST_B3V = 6, ST_B3H = 7,
-    ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11, ST_PHASE_A_TILE = 12, ST_PHASE_B_TILE = 13
+    ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11, ST_PHASE_A_TILE = 12, ST_PHASE_B_TILE = 13,
+    ST_PHASE_A_WARP = 18, ST_PHASE_B_WARP = 19
 };
 
 bool cuda_ok(cudaError_t e, const char *what);
@@ -19,11 +20,14 @@ bool launch_stage(int stage, int vec, const Arrays &A, const MeshDev &M, const i
 // tile-staged fused phase (stage = ST_PHASE_A / ST_PHASE_B) over node set `which`:
 // 0 all owned nodes, 1 boundary list, 2 interior list
 bool launch_tile(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s);
+// warp-item fused phase (fct_warp_kernels.cuh), same arguments
+bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s);
 Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, const int *nlev_e,
                        const int *elem_nodes, const int *nie_num, const int *nie, int nie_dim,
                        const int *edges, const int *edge_tri);
 void destroy_plan(Plan *p);
 
+static const int FCT_FIELD_COUNT_INTERNAL = 17;   // == FCT_FIELD_COUNT of the public header
 static const unsigned FIELDS_MAGIC = 0x464c4453u;
 static const unsigned HALO_MAGIC = 0x48414c4fu;
 static const unsigned PLAN_MAGIC = 0x504c414eu;
@@ -34,7 +38,7 @@ struct Fields {
     int T = 0;         // tracers
     int P = 0;         // row pitch (doubles)
     size_t rows = 0;   // N + H
-    double *buf[16] = {nullptr};
+    double *buf[FCT_FIELD_COUNT_INTERNAL] = {nullptr};
     size_t ts_node = 0, ts_edge = 0, ts_uv = 0;
 };
 

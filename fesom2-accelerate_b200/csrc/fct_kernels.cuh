@@ -21,6 +21,7 @@ struct Arrays {
     // per-tracer arrays: pointer to tracer 0, blockIdx.y selects the tracer
     const double *ttf, *lo;
     double *adf_v;
+    double *adf_v_out;   // limited vertical fluxes of the fused kernels (== adf_v: in place)
     const double *adf_h_in;
     double *adf_h_out;
     double *ttf_max, *ttf_min, *plus, *minus, *del_v, *del_h;
@@ -666,7 +667,7 @@ __global__ void k_phaseB(Arrays A, MeshDev M, const int *list, int first, int co
     double fo[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) fo[v] = fl[v];
-    stv<VEC>(vrow + z0, fo, cnt);
+    stv<VEC>(A.adf_v_out + blockIdx.y * A.ts_nodev + (size_t)n * A.pitchV + z0, fo, cnt);
     stv<VEC>(A.del_v + off, dv, cnt);
     stv<VEC>(A.del_h + off, dh, cnt);
 }

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 namespace fct {
 
@@ -190,4 +191,229 @@ bool build_tileset(const DerivedHost &d, const int *nlev_n, int N, int NT, const
     return true;
 }
 
+
+// ---- warp-item tiles -------------------------------------------------------------------------------
+namespace {
+struct StagedRow {
+    unsigned goff;   // global element offset of the row
+    int soff;        // byte offset inside its staging region
+    int bytes;
+};
+inline int pad16(int b) { return (b + 15) & ~15; }
+inline int row_bytes(int levels) { return ((std::max(levels, 0) + 1) & ~1) * 8; }
+}   // namespace
+
+bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P,
+                     const std::vector<int> *list, int TN, int nch, int smem_cap, WarpTilesHost &out)
+{
+    const int count = list ? (int)list->size() : N;
+    const int W = 32 * nch;
+    out = WarpTilesHost();
+    out.blob_off.assign(1, 0u);
+    if (P > 256 || (P & 1) || TN < 1 || TN > 255) return false;
+    if ((long long)NT * P >= (1LL << 32) || (long long)G * P >= (1LL << 32)) return false;
+    if (d.nbr_off.size() != (size_t)N + 1) return false;
+    const int slack = P * 8 + 32;   // masked lanes read up to one row past the last staged byte
+    std::vector<int> nstamp((size_t)NT, -1), nsoff((size_t)NT, 0), estamp((size_t)std::max(G, 1), -1), esoff((size_t)std::max(G, 1), 0);
+    std::vector<StagedRow> rows, erows;
+    std::vector<int4> hdr, ent;
+    std::vector<unsigned short> sched;
+    std::vector<std::pair<int, int>> a, b;
+    std::vector<char> checked((size_t)N, 0);
+
+    auto need_bytes = [&](size_t nrows, size_t nerows, size_t nn, size_t nent, size_t nsched, int rb, int eb) {
+        const size_t blob = WT_HDR_BYTES + pad16((int)nrows * 8) + pad16((int)nerows * 8) + nn * 16 + nent * 16 +
+                            pad16((int)((nsched + W - 1) / W * W) * 2);
+        return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack;
+    };
+
+    int pos = 0, tile = 0;
+    while (pos < count) {
+        rows.clear();
+        erows.clear();
+        hdr.clear();
+        ent.clear();
+        sched.clear();
+        int rb = 0, eb = 0, nn = 0;
+        while (pos < count && nn < TN) {
+            const int n = list ? (*list)[pos] : pos;
+            if (n < 0 || n >= N) return false;
+            const int nz = std::max(nlev_n[n] - 1, 0);
+            const int e0 = d.edg_off[n], e1 = d.edg_off[n + 1];
+            const int cnt = e1 - e0;
+            if (nz > 254 || cnt > 255) return false;
+            if (!checked[n]) {
+                // triangulation check: {ring neighbours} == {other ends of the edges}, same depths,
+                // and no edge deeper than either of its end columns (what the reference's own
+                // loops assume: reference.cpp:412-423 index the node rows down to the edge depth)
+                const int nb0 = d.nbr_off[n], nb1 = d.nbr_off[n + 1];
+                if (nb1 - nb0 < 1 || d.nbr[nb0].x != n) return false;
+                a.clear();
+                b.clear();
+                for (int k = nb0 + 1; k < nb1; ++k) a.emplace_back(d.nbr[k].x, d.nbr[k].y);
+                for (int k = e0; k < e1; ++k) {
+                    const int m = d.edg[k].y, dg = FCT_META_DEPTH(d.edg[k].z);
+                    if (m == n || m < 0 || m >= NT) return false;
+                    if (dg > nz || dg > std::max(nlev_n[m] - 1, 0)) return false;
+                    b.emplace_back(m, dg);
+                }
+                std::sort(a.begin(), a.end());
+                std::sort(b.begin(), b.end());
+                if (a != b) return false;
+                for (size_t k = 1; k < b.size(); ++k)
+                    if (b[k].first == b[k - 1].first) return false;
+                if ((d.nbr[nb0].y) > nz) return false;
+                checked[n] = 1;
+            }
+            // ---- footprint if this node joins the tile ----
+            int add_rb = 0, add_eb = 0;
+            size_t add_rows = 0, add_erows = 0;
+            if (nstamp[n] != tile) {
+                add_rb += row_bytes(nz);
+                ++add_rows;
+            }
+            for (int k = e0; k < e1; ++k) {
+                const int m = d.edg[k].y, g = d.edg[k].x;
+                if (nstamp[m] != tile) {
+                    add_rb += row_bytes(nlev_n[m] - 1);
+                    ++add_rows;
+                }
+                if (estamp[g] != tile) {
+                    add_eb += row_bytes(FCT_META_DEPTH(d.edg[k].z));
+                    ++add_erows;
+                }
+            }
+            const int s = (nz + 1) / 2;
+            if (s > W) return false;
+            size_t nsched = sched.size();
+            if (s > 0 && (int)(nsched % W) + s > W) nsched = (nsched + W - 1) / W * W;
+            nsched += s;
+            const size_t need = need_bytes(rows.size() + add_rows, erows.size() + add_erows, nn + 1, ent.size() + cnt,
+                                           nsched, rb + add_rb, eb + add_eb);
+            if ((int)need > smem_cap || ent.size() + cnt > 65535) {
+                if (nn == 0) return false;
+                break;
+            }
+            // ---- commit ----
+            auto touch = [&](int m) {
+                if (nstamp[m] != tile) {
+                    nstamp[m] = tile;
+                    nsoff[m] = rb;
+                    const int bytes = row_bytes(nlev_n[m] - 1);
+                    rows.push_back({(unsigned)((long long)m * P), rb, bytes});
+                    rb += bytes;
+                }
+                return nsoff[m];
+            };
+            const int own = touch(n);
+            hdr.push_back(make_int4((int)((long long)n * P), nz | (std::min(std::max(d.fillmin[n], 0), 255) << 8) | ((d.nbr[d.nbr_off[n]].y & 0xff) << 16),
+                                    own, (int)ent.size() | (cnt << 16)));
+            for (int k = e0; k < e1; ++k) {
+                const int4 e = d.edg[k];
+                const int other = touch(e.y);
+                if (estamp[e.x] != tile) {
+                    estamp[e.x] = tile;
+                    esoff[e.x] = eb;
+                    const int bytes = row_bytes(FCT_META_DEPTH(e.z));
+                    erows.push_back({(unsigned)((long long)e.x * P), eb, bytes});
+                    eb += bytes;
+                }
+                const unsigned meta = (unsigned)FCT_META_DEPTH(e.z) | (FCT_META_WRITER(e.z) ? 0x40000000u : 0u) |
+                                      (FCT_META_SECOND(e.z) ? 0x80000000u : 0u);
+                ent.push_back(make_int4(esoff[e.x], other, (int)meta, (int)((long long)e.x * P)));
+            }
+            if (s > 0 && (int)(sched.size() % W) + s > W) sched.resize((sched.size() + W - 1) / W * W, (unsigned short)WT_IDLE);
+            for (int i = 0; i < s; ++i) sched.push_back((unsigned short)(nn | (i << 8)));
+            out.slots += s;
+            out.edge_uses += cnt;
+            ++nn;
+            ++pos;
+        }
+        sched.resize((sched.size() + W - 1) / W * W, (unsigned short)WT_IDLE);
+        // ---- assemble the blob ----
+        const int off_rows = WT_HDR_BYTES;
+        const int off_erows = off_rows + pad16((int)rows.size() * 8);
+        const int off_hdr = off_erows + pad16((int)erows.size() * 8);
+        const int off_ent = off_hdr + (int)hdr.size() * 16;
+        const int off_sched = off_ent + (int)ent.size() * 16;
+        const int blob_bytes = off_sched + pad16((int)sched.size() * 2);
+        long long tx = 0;
+        for (auto &r : rows) tx += 2LL * r.bytes;
+        for (auto &r : erows) tx += r.bytes;
+        if (tx >= (1 << 20)) return false;   // mbarrier transaction-count range
+        std::vector<unsigned char> buf((size_t)blob_bytes, 0);
+        int *h = reinterpret_cast<int *>(buf.data());
+        h[0] = (int)rows.size();
+        h[1] = (int)erows.size();
+        h[2] = nn;
+        h[3] = (int)sched.size() / W;
+        h[4] = off_erows;
+        h[5] = off_hdr;
+        h[6] = off_ent;
+        h[7] = off_sched;
+        h[8] = blob_bytes;
+        h[9] = rb;
+        h[10] = eb;
+        h[11] = (int)tx;
+        auto put_rows = [&](const std::vector<StagedRow> &v, int off) {
+            int2 *t = reinterpret_cast<int2 *>(buf.data() + off);
+            for (size_t i = 0; i < v.size(); ++i) t[i] = make_int2((int)v[i].goff, (v[i].soff >> 4) | ((v[i].bytes >> 4) << 16));
+        };
+        put_rows(rows, off_rows);
+        put_rows(erows, off_erows);
+        if (!hdr.empty()) std::memcpy(buf.data() + off_hdr, hdr.data(), hdr.size() * 16);
+        if (!ent.empty()) std::memcpy(buf.data() + off_ent, ent.data(), ent.size() * 16);
+        if (!sched.empty()) std::memcpy(buf.data() + off_sched, sched.data(), sched.size() * 2);
+        const size_t at = out.blob.size();
+        out.blob.resize(at + (size_t)blob_bytes / 16);
+        std::memcpy(out.blob.data() + at, buf.data(), (size_t)blob_bytes);
+        out.blob_off.push_back((unsigned)out.blob.size());
+        out.smem_bytes = std::max(out.smem_bytes, 16 + blob_bytes + 2 * rb + eb + slack);
+        out.nodes += nn;
+        out.staged_rows += (long long)rows.size();
+        out.staged_erows += (long long)erows.size();
+        out.lanes += (long long)sched.size();
+        ++tile;
+    }
+    out.ntiles = tile;
+    return true;
+}
+
 }   // namespace fct
+
+// Host-only introspection of the inspector (no CUDA device needed): builds the gather lists and the
+// warp-item tile blobs of one node set and copies them out, so that the tables the kernels consume
+// can be checked on a CPU box (tests/test_warp_plan.py interprets them with numpy).
+extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D, int *myDim_edge2D,
+                                      int *nl, int *nlevels_nod2D, int *nlevels_elem2D, int *elem2D_nodes,
+                                      int *nod_in_elem2D_num, int *nod_in_elem2D, int *nod_in_elem2D_dim,
+                                      int *edges, int *edge_tri, int *tile_nodes, int *nch, int *smem_cap,
+                                      int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
+                                      unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat)
+{
+    using namespace fct;
+    *istat = 1;
+    *ntiles = 0;
+    *smem_bytes = 0;
+    DerivedHost d;
+    const int N = *myDim_nod2D, H = *eDim_nod2D;
+    if (!build_derived(N, H, *myDim_elem2D, *myDim_edge2D, *nl, nlevels_elem2D, elem2D_nodes, nod_in_elem2D_num,
+                       nod_in_elem2D, *nod_in_elem2D_dim, edges, edge_tri, d))
+        return;
+    const std::vector<int> *list = *which == 1 ? &d.boundary : (*which == 2 ? &d.interior : nullptr);
+    WarpTilesHost h;
+    const int P = (*nl + 1) & ~1;
+    if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, list, *tile_nodes, *nch, *smem_cap, h)) {
+        *istat = 2;   // mesh not eligible
+        return;
+    }
+    *ntiles = h.ntiles;
+    *smem_bytes = h.smem_bytes;
+    if ((long long)h.blob.size() * 4 > *blob_capacity || h.ntiles + 1 > *tiles_capacity) {
+        *istat = 3;   // caller's buffers too small
+        return;
+    }
+    std::memcpy(blob, h.blob.data(), h.blob.size() * 16);
+    std::memcpy(blob_off, h.blob_off.data(), h.blob_off.size() * sizeof(unsigned));
+    *istat = 0;
+}

@@ -6,6 +6,7 @@
 
 #include "fct_kernels.cuh"
 #include "fct_tile_kernels.cuh"
+#include "fct_warp_kernels.cuh"
 
 namespace fct {
 
@@ -41,6 +42,23 @@ struct TileSetHost {
 bool build_tileset(const DerivedHost &d, const int *nlev_n, int N, int NT, const std::vector<int> *list,
                    int TN, int TE, int vec, int threads, int budget, TileSetHost &out);
 
+// Per-tile blobs of the warp-item kernels (see fct_warp_kernels.cuh), for one node list.
+struct WarpTilesHost {
+    std::vector<uint4> blob;
+    std::vector<unsigned> blob_off;   // 16-byte units
+    int ntiles = 0, smem_bytes = 0;
+    // statistics (FCT_VERBOSE)
+    long long nodes = 0, staged_rows = 0, staged_erows = 0, edge_uses = 0, slots = 0, lanes = 0;
+};
+// Greedy tiling of `list` (nullptr: the identity 0..N-1): a tile closes after TN nodes or when its
+// shared-memory footprint (blob + two staged node-row regions + the edge-row region) would exceed
+// smem_cap.  `nch`: virtual-lane chunks per lane (a warp item has 32*nch slots of two levels).
+// Returns false when the mesh is not a plain triangulation (ring neighbours == edge neighbours
+// with equal depths, every edge at most as deep as both of its end nodes), a column does not fit
+// a warp item or an offset does not fit its field: the caller then keeps the other kernels.
+bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P,
+                     const std::vector<int> *list, int TN, int nch, int smem_cap, WarpTilesHost &out);
+
 struct Plan {
     unsigned magic = 0x504c414eu;
     int N = 0, H = 0, E = 0, G = 0, nl = 0, nie_dim = 0;
@@ -52,6 +70,10 @@ struct Plan {
     // tile-staged fused kernels: [phase A / B][0 all owned nodes, 1 boundary list, 2 interior list]
     TileDev tiles[2][3] = {};
     bool tiles_ok = false;
+    // warp-item kernels: one tile set serves both phases; [0 all owned, 1 boundary, 2 interior]
+    WarpTilesDev wtiles[3] = {};
+    int wt_nch = 1;
+    bool wtiles_ok = false;
     std::vector<void *> owned;   // device allocations to free
 };
 

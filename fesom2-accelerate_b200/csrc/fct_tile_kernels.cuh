@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) k_phaseB_tile(Arrays A, Ti
         double fo[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) fo[v] = fl[v];
-        stv<VEC>(vrow + z0, fo, c);
+        stv<VEC>(A.adf_v_out + (vrow - A.adf_v) + z0, fo, c);
         stv<VEC>(A.del_v + off, dv, c);
         stv<VEC>(A.del_h + off, dh, c);
     }

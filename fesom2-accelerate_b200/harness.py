@@ -250,21 +250,24 @@ class DeviceFields:
         for k in names:
             self.upload_field(k, getattr(f, k), tracer)
         if outputs:
+            # cells the kernels never write keep the input values, like the reference's in-place update
             self.upload_field("fct_adf_h_out", f.fct_adf_h, tracer)
+            self.upload_field("fct_adf_v_out", f.fct_adf_v, tracer)
         self.stream.sync()
 
     def download(self, f: Fields, tracer: int = 0, mode: int = 1, names=None) -> Fields:
-        """Fetch results into (a copy of) `f`; the limited horizontal fluxes come from the OUT
-        buffer in fused mode."""
+        """Fetch results into (a copy of) `f`; the limited fluxes come from the OUT buffers in the
+        fused modes."""
         out = f.copy()
         if names is None:
-            names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v",
+            names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus",
                      "del_ttf_advvert", "del_ttf_advhoriz"]
             if mode == 0 and self.with_uv and f.UV_rhs is not None:
                 names.append("UV_rhs")
+            self.download_field("fct_adf_h_out" if mode >= 1 else "fct_adf_h", out.fct_adf_h, tracer)
+            self.download_field("fct_adf_v_out" if mode >= 1 else "fct_adf_v", out.fct_adf_v, tracer)
         for k in names:
             self.download_field(k, getattr(out, k), tracer)
-        self.download_field("fct_adf_h_out" if mode >= 1 else "fct_adf_h", out.fct_adf_h, tracer)
         self.stream.sync()
         return out
 

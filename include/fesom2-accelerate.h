@@ -188,6 +188,16 @@ void fct_ale_plan_create_(void **plan, int *myDim_nod2D, int *eDim_nod2D, int *m
                           int *elem2D_nodes, int *nod_in_elem2D_num, int *nod_in_elem2D,
                           int *nod_in_elem2D_dim, int *edges, int *edge_tri, int *istat);
 void fct_ale_plan_destroy_(void **plan, int *istat);
+/* Host-only introspection of the inspector (no CUDA device needed): the warp-item tile tables the
+ * fused kernels consume for node set *which (0 all owned, 1 boundary, 2 interior), as 32-bit words
+ * (layout: fesom2-accelerate_b200/csrc/fct_warp_kernels.cuh).  *istat: 0 ok, 1 malformed mesh,
+ * 2 mesh not eligible for the warp-item kernels, 3 buffers too small. */
+void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D, int *myDim_edge2D,
+                           int *nl, int *nlevels_nod2D, int *nlevels_elem2D, int *elem2D_nodes,
+                           int *nod_in_elem2D_num, int *nod_in_elem2D, int *nod_in_elem2D_dim,
+                           int *edges, int *edge_tri, int *tile_nodes, int *nch, int *smem_cap,
+                           int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
+                           unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat);
 /* pitch (in doubles) of every padded device row of this plan: nl rounded up to an even count */
 void fct_ale_plan_pitch_(void **plan, int *pitch);
 
@@ -201,7 +211,7 @@ enum fct_field_id {
     FCT_TTF = 0, FCT_LO = 1, FCT_ADF_V = 2, FCT_ADF_H = 3, FCT_AREA = 4, FCT_AREA_INV = 5,
     FCT_HNODE = 6, FCT_HNODE_NEW = 7, FCT_DEL_V = 8, FCT_DEL_H = 9, FCT_TTF_MAX = 10,
     FCT_TTF_MIN = 11, FCT_PLUS = 12, FCT_MINUS = 13, FCT_UV_RHS = 14, FCT_ADF_H_OUT = 15,
-    FCT_FIELD_COUNT = 16
+    FCT_ADF_V_OUT = 16, FCT_FIELD_COUNT = 17
 };
 /* dense host array (the Fortran layout above) <-> padded device rows of tracer *tracer
  * (mesh-static fields area / area_inv / hnode / hnode_new ignore *tracer).  Asynchronous on
@@ -212,19 +222,22 @@ void fct_ale_field_download_(void **fields, int *field, int *tracer, real_type *
                              int *istat);
 
 /* One fct_ale step a1..c over all tracers of `fields`, everything resident on the device.
- *   *mode 0: ten stage kernels (one per reference kernel);  *mode 1: two fused phase kernels,
- *   tile-staged through shared memory when the plan's tiles fit;  *mode 2: the fused kernels
- *   without tile staging (measured alternative).
+ *   *mode 0: ten stage kernels (one per reference kernel);  *mode 1: two fused phase kernels, the
+ *   fastest variant the plan supports (TMA-staged warp-item kernels on plain triangulations, else
+ *   the tile-staged, else the untiled ones);  *mode 2: the untiled fused kernels;  *mode 3: the
+ *   tile-staged fused kernels (modes 2 and 3 are measured alternatives).
  * When `halo` is non-null the fct_plus / fct_minus halo exchange runs between b2 and b3
  * horizontal over NVLink, overlapped with the interior nodes' phase B work.
- * The limited horizontal fluxes are written to the FCT_ADF_H_OUT buffer in modes 1 and 2 (the in-place
- * update of the reference would race between the two end nodes of an edge) and in place
- * (FCT_ADF_H) in mode 0.  *alg_state = 10 on success. */
+ * In the fused modes (1, 2, 3) the limited fluxes are written to the FCT_ADF_H_OUT / FCT_ADF_V_OUT
+ * buffers (an in-place update would race with the neighbouring threads that still read the raw
+ * values); mode 0 updates FCT_ADF_H / FCT_ADF_V in place like the reference.  *alg_state = 10 on
+ * success. */
 void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_type *dt,
                    real_type *flux_eps, real_type *bignumber, int *alg_state);
 /* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,
  * 6 b3v, 7 b3h, 8 c_v, 9 c_h; 10 fused phase A, 11 fused phase B; 12 / 13 the tile-staged
- * fused phases */
+ * fused phases (14-17: their boundary / interior subsets); 18 / 19 the warp-item fused phases
+ * (20 / 21: phase A on the boundary / interior tiles, 22 / 23: phase B) */
 void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, real_type *flux_eps,
                     real_type *bignumber, int *istat);
 

@@ -26,6 +26,9 @@ def check(got, want, keys=OUT_KEYS, exact=True, owned=None):
 
 
 def cases(mesh_mod, name):
+    if name == "deep":        # DART-depth columns: two virtual-lane chunks per lane in the warp-item kernels
+        m = mesh_mod.make_mesh(48, 37, 80, seed=3)
+        return m, mesh_mod.make_fields(m, seed=4)
     if name == "adversarial":
         return mesh_mod.adversarial_case(300, 17, seed=5)
     if name == "adversarial_even":
@@ -56,9 +59,11 @@ def test_handle_abi_chain(mesh_mod, harness, abi, oracle_mod, name, fused):
         assert bits_equal(dev["UV_rhs"], want.UV_rhs)
 
 
-@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "adversarial", "adversarial_even"])
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "deep", "adversarial", "adversarial_even"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
+    """mode 0: ten stage kernels; 1: fastest fused variant of the plan (TMA-staged warp-item kernels on
+    triangulations); 2: untiled fused kernels; 3: tile-staged fused kernels."""
     m, f = cases(mesh_mod, name)
     want = f.copy()
     oracle_mod.fct_ale(m, want)
@@ -73,6 +78,32 @@ def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
         assert bits_equal(got.UV_rhs, want.UV_rhs)
     df.free()
     plan.free()
+
+
+@pytest.mark.parametrize("name", ["pi", "deep"])
+@pytest.mark.parametrize("knobs", [dict(WT_NCH=2), dict(WT_NODES=5), dict(WT_NODES=200, WT_SMEM=200 * 1024),
+                                   dict(WT_MINB_A=1, WT_MINB_B=1)])
+def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, knobs):
+    """The warp-item kernels must not depend on their tiling: chunk count, tile size (tiny tiles:
+    almost every neighbour row is a halo row; one huge tile per CTA), register bound."""
+    m, f = cases(mesh_mod, name)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    defaults = dict(WT_NCH=0, WT_NODES=0, WT_SMEM=0, WT_MINB_A=0, WT_MINB_B=0)
+    try:
+        for k, v in knobs.items():
+            abi.tune(k, v)
+        plan = harness.DevicePlan(m)
+        df = harness.DeviceFields(plan, 1, with_uv=False)
+        df.upload(f)
+        df.stage("phaseA_warp", f)       # fails loudly if the plan has no warp tiles
+        df.stage("phaseB_warp", f)
+        check(df.download(f, mode=1), want)
+        df.free()
+        plan.free()
+    finally:
+        for k, v in defaults.items():
+            abi.tune(k, v)
 
 
 def test_stage_by_stage(mesh_mod, harness, oracle_mod):
@@ -175,7 +206,7 @@ def test_step_is_repeatable_and_deterministic(mesh_mod, harness):
 
 
 @pytest.mark.parametrize("nparts", [2, 5])
-@pytest.mark.parametrize("tiled", [False, True])
+@pytest.mark.parametrize("tiled", [False, True, "warp"])
 def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled):
     """Every partition of a mesh run on this GPU with the halo exchange emulated through the host:
     owned results of all partitions must reproduce the single-domain oracle bit for bit (boundary /
@@ -189,6 +220,9 @@ def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled):
     dfs = [harness.DeviceFields(pl, 1, with_uv=False) for pl in plans]
     stA = ["phaseA_tile_boundary", "phaseA_tile_interior"] if tiled else ["phaseA"]
     stB = ["phaseB_tile_interior", "phaseB_tile_boundary"] if tiled else ["phaseB"]
+    if tiled == "warp":
+        stA = ["phaseA_warp_boundary", "phaseA_warp_interior"]
+        stB = ["phaseB_warp_interior", "phaseB_warp_boundary"]
     for df, lf in zip(dfs, lfs):
         df.upload(lf)
         for s in stA:

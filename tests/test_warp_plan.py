@@ -1,0 +1,326 @@
+"""Host logic of the warp-item kernels, checked without a GPU: the inspector's per-tile tables
+(fct_ale_plan_inspect_, a host-only entry point of the product library) are interpreted by a small
+numpy/Python executor that follows fct_warp_kernels.cuh step by step -- bulk copies of the listed
+rows into a byte image of the CTA's shared memory, the in-place a1 pass, the warp-item schedule,
+the neighbour lookups through precomputed byte offsets, the virtual-lane stencil -- and the result
+is compared with the oracle.  A wrong offset, depth, role flag, schedule or summation order in the
+tables shows up here before any kernel runs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+INF = float("inf")
+
+
+def inspect(abi, m, tile_nodes=64, nch=1, smem_cap=74 * 1024, which=0):
+    lib = abi.load()
+    cap_words = 64 * 1024 * 1024 // 4
+    blob = np.zeros(cap_words, np.uint32)
+    off = np.zeros(m.myDim_nod2D + 2, np.uint32)
+    nt, sm, st = C.c_int(), C.c_int(), C.c_int()
+    u32p = C.POINTER(C.c_uint32)
+    lib.fct_ale_plan_inspect_(
+        abi.ci(m.myDim_nod2D), abi.ci(m.eDim_nod2D), abi.ci(m.myDim_elem2D), abi.ci(m.myDim_edge2D),
+        abi.ci(m.nl), abi.iptr(m.nlevels_nod2D), abi.iptr(m.nlevels_elem),
+        abi.iptr(m.elem2D_nodes.reshape(-1)), abi.iptr(m.nod_in_elem2D_num),
+        abi.iptr(m.nod_in_elem2D.reshape(-1)), abi.ci(m.nod_in_elem2D_dim), abi.iptr(m.edges.reshape(-1)),
+        abi.iptr(m.edge_tri.reshape(-1)), abi.ci(tile_nodes), abi.ci(nch), abi.ci(smem_cap), abi.ci(which),
+        C.byref(C.c_longlong(cap_words * 4)), blob.ctypes.data_as(u32p), abi.ci(off.size),
+        off.ctypes.data_as(u32p), C.byref(nt), C.byref(sm), C.byref(st))
+    return st.value, nt.value, sm.value, blob, off
+
+
+class Tile:
+    """Decoded blob of one tile + the shared-memory image the kernels build from it."""
+
+    def __init__(self, words, P, nch):
+        b = words.tobytes()
+        h = np.frombuffer(b, np.int32, 16)
+        (self.n_rows, self.n_erows, self.n_nodes, self.n_witems, off_erows, off_hdr, off_ent, off_sched,
+         blob_bytes, self.rows_bytes, self.erows_bytes, self.tx) = [int(x) for x in h[:12]]
+        assert blob_bytes == len(b)
+        self.rows = np.frombuffer(b, np.uint32, 2 * self.n_rows, 64).reshape(-1, 2)
+        self.erows = np.frombuffer(b, np.uint32, 2 * self.n_erows, off_erows).reshape(-1, 2)
+        self.hdr = np.frombuffer(b, np.uint32, 4 * self.n_nodes, off_hdr).reshape(-1, 4)
+        n_ent = (off_sched - off_ent) // 16
+        self.ent = np.frombuffer(b, np.uint32, 4 * n_ent, off_ent).reshape(-1, 4)
+        self.sched = np.frombuffer(b, np.uint16, self.n_witems * 32 * nch, off_sched).reshape(self.n_witems, 32 * nch)
+        self.P = P
+
+    def stage(self, src_a, src_b, src_e):
+        """the bulk copies of wt_stage: returns (rowsA, rowsB, erows) as float64 images (NaN = never written)"""
+        A = np.full(self.rows_bytes // 8 + 2 * self.P, np.nan)
+        B = A.copy()
+        Ee = np.full(self.erows_bytes // 8 + 2 * self.P, np.nan)
+        tx = 0
+        for goff, pk in self.rows:
+            so, sz = (int(pk) & 0xffff) * 2, (int(pk) >> 16) * 2       # in doubles
+            assert so + sz <= self.rows_bytes // 8
+            A[so:so + sz] = src_a[goff:goff + sz]
+            B[so:so + sz] = src_b[goff:goff + sz]
+            tx += 2 * sz * 8
+        for goff, pk in self.erows:
+            so, sz = (int(pk) & 0xffff) * 2, (int(pk) >> 16) * 2
+            assert so + sz <= self.erows_bytes // 8
+            Ee[so:so + sz] = src_e[goff:goff + sz]
+            tx += sz * 8
+        assert tx == self.tx
+        return A, B, Ee
+
+
+def pmax(a, b):
+    return b if a < b else a
+
+
+def pmin(a, b):
+    return b if b < a else a
+
+
+def pad(a, P):
+    out = np.zeros((a.shape[0], P))
+    out[:, :a.shape[1]] = a
+    return out.reshape(-1)
+
+
+def emulate(m, f, blob, off, ntiles, nch):
+    """Both fused phases on the padded layout; returns the dict of padded result arrays."""
+    P = (m.nl + 1) & ~1
+    L = m.L
+    g = {k: pad(getattr(f, k), P) for k in ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area", "area_inv", "hnode",
+                                            "hnode_new", "del_ttf_advvert", "del_ttf_advhoriz", "fct_ttf_max",
+                                            "fct_ttf_min", "fct_plus", "fct_minus")}
+    g["adf_v_out"] = g["fct_adf_v"].copy()
+    g["adf_h_out"] = g["fct_adf_h"].copy()
+    dt, eps, big = f.dt, f.flux_eps, f.bignumber
+    W = 32 * nch
+    seen_slots = set()
+    for phase in "AB":
+        for t in range(ntiles):
+            T = Tile(blob[off[t] * 4: off[t + 1] * 4], P, nch)
+            if phase == "A":
+                RA, RB, RE = T.stage(g["fct_LO"], g["ttf"], g["fct_adf_h"])
+                lo_, tt_ = RA.copy(), RB.copy()
+                with np.errstate(invalid="ignore"):
+                    RA = np.where(lo_ < tt_, tt_, lo_)           # pick_max(lo, ttf)
+                    RB = np.where(tt_ < lo_, tt_, lo_)           # pick_min(lo, ttf)
+            else:
+                RA, RB, RE = T.stage(g["fct_plus"], g["fct_minus"], g["fct_adf_h"])
+            for wi in range(T.n_witems):
+                lanes = []
+                for vl in range(W):
+                    d = int(T.sched[wi, vl])
+                    if d == 0xffff:
+                        lanes.append(None)
+                        continue
+                    ln, z0 = d & 0xff, (d >> 8) * 2
+                    hx, hy, hz, hw = [int(x) for x in T.hdr[ln]]
+                    lanes.append(dict(ln=ln, z0=z0, grow=hx + z0, nz=hy & 0xff, fm=(hy >> 8) & 0xff, sd=(hy >> 16) & 0xff,
+                                      own=hz // 8, e0=hw & 0xffff, cnt=hw >> 16))
+                    if phase == "A":
+                        assert (t, ln, z0) not in seen_slots
+                        seen_slots.add((t, ln, z0))
+                # slots of a node are consecutive virtual lanes and complete
+                for vl, s in enumerate(lanes):
+                    if s is None:
+                        continue
+                    assert s["z0"] < s["nz"]
+                    if s["z0"] > 0:
+                        q = lanes[vl - 1]
+                        assert vl > 0 and q is not None and q["ln"] == s["ln"] and q["z0"] == s["z0"] - 2
+                    if s["z0"] + 2 < s["nz"]:
+                        q = lanes[vl + 1] if vl + 1 < W else None
+                        assert q is not None and q["ln"] == s["ln"] and q["z0"] == s["z0"] + 2
+                if phase == "A":
+                    phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big)
+                else:
+                    phase_b_item(T, lanes, RA, RB, RE, g, dt)
+    return g, P
+
+
+def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
+    tv = []
+    for s in lanes:
+        if s is None:
+            tv.append(None)
+            continue
+        z0, nz = s["z0"], s["nz"]
+        hi = [(-big if z0 + v >= s["fm"] else -INF) for v in range(2)]
+        lw = [(big if z0 + v >= s["fm"] else INF) for v in range(2)]
+        fv = g["fct_adf_v"]
+        f0, f1 = fv[s["grow"]], fv[s["grow"] + 1]
+        f2 = fv[s["grow"] + 2] if z0 + 2 <= nz else 0.0
+        for v in range(2):
+            if z0 + v < s["sd"]:
+                hi[v] = pmax(hi[v], RA[s["own"] + z0 + v])
+                lw[v] = pmin(lw[v], RB[s["own"] + z0 + v])
+        p = [pmax(0., f0) + pmax(0., -f1), pmax(0., f1) + pmax(0., -f2)]
+        mm = [pmin(0., f0) + pmin(0., -f1), pmin(0., f1) + pmin(0., -f2)]
+        for k in range(s["cnt"]):
+            ex, ey, ez, ew = [int(x) for x in T.ent[s["e0"] + k]]
+            dg, second = ez & 0xffff, bool(ez >> 31)
+            for v in range(2):
+                if z0 + v < dg:
+                    x, y, h = RA[ey // 8 + z0 + v], RB[ey // 8 + z0 + v], RE[ex // 8 + z0 + v]
+                    assert not (np.isnan(x) or np.isnan(y) or np.isnan(h)), "read of a byte that was never staged"
+                    hi[v] = pmax(hi[v], x)
+                    lw[v] = pmin(lw[v], y)
+                    q = -h if second else h
+                    p[v] += pmax(0., q)
+                    mm[v] += pmin(0., q)
+        s.update(hi=hi, lw=lw, p=p, m=mm)
+        tv.append(s)
+    for vl, s in enumerate(tv):
+        if s is None:
+            continue
+        z0, nz = s["z0"], s["nz"]
+        for v in range(2):
+            z = z0 + v
+            if z >= nz:
+                continue
+            x, y = s["hi"][v], s["lw"][v]
+            if 0 < z < nz - 1:
+                if v == 0:
+                    pv = tv[vl - 1]
+                    x = pmax(pmax(pv["hi"][1], x), s["hi"][1])
+                    y = pmin(pmin(pv["lw"][1], y), s["lw"][1])
+                else:
+                    nv = tv[vl + 1]
+                    x = pmax(pmax(s["hi"][0], x), nv["hi"][0])
+                    y = pmin(pmin(s["lw"][0], y), nv["lw"][0])
+            o = s["grow"] + v
+            l, ai = g["fct_LO"][o], g["area_inv"][o]
+            bm, bn = x - l, y - l
+            with np.errstate(all="ignore"):
+                pf = pmin(1., float(np.float64(bm) / np.float64(s["p"][v] * dt * ai + eps)))
+                mf = pmin(1., float(np.float64(bn) / np.float64(s["m"][v] * dt * ai - eps)))
+            g["fct_ttf_max"][o], g["fct_ttf_min"][o], g["fct_plus"][o], g["fct_minus"][o] = bm, bn, pf, mf
+
+
+def phase_b_item(T, lanes, RA, RB, RE, g, dt):
+    for s in lanes:
+        if s is None:
+            continue
+        z0, nz, own = s["z0"], s["nz"], s["own"]
+        fv = g["fct_adf_v"]
+
+        def lim(z):
+            fz = fv[s["grow"] - z0 + z]
+            if z >= nz:
+                return fz
+            ae = 1.
+            if z == 0:
+                ae = pmin(ae, RA[own] if fz >= 0. else RB[own])
+            elif fz >= 0.:
+                ae = pmin(pmin(ae, RB[own + z - 1]), RA[own + z])
+            else:
+                ae = pmin(pmin(ae, RA[own + z - 1]), RB[own + z])
+            return ae * fz
+        fl = [lim(z0), lim(z0 + 1), lim(z0 + 2) if z0 + 2 <= nz else 0.]
+        out = {}
+        for v in range(2):
+            if z0 + v >= nz:
+                continue
+            o = s["grow"] + v
+            ar = dt / g["area"][o]
+            dv = (g["del_ttf_advvert"][o] - g["ttf"][o] * g["hnode"][o] + g["fct_LO"][o] * g["hnode_new"][o]
+                  + (fl[v] - fl[v + 1]) * ar)
+            out[v] = [ar, dv, g["del_ttf_advhoriz"][o]]
+        for k in range(s["cnt"]):
+            ex, ey, ez, ew = [int(x) for x in T.ent[s["e0"] + k]]
+            dg, second, writer = ez & 0xffff, bool(ez >> 31), bool((ez >> 30) & 1)
+            for v in range(2):
+                z = z0 + v
+                if z >= dg:
+                    continue
+                h, po, mo = RE[ex // 8 + z], RA[ey // 8 + z], RB[ey // 8 + z]
+                pn, mn = RA[own + z], RB[own + z]
+                assert not (np.isnan(h) or np.isnan(po) or np.isnan(mo) or np.isnan(pn) or np.isnan(mn))
+                p1, m1, p2, m2 = (po, mo, pn, mn) if second else (pn, mn, po, mo)
+                ae = pmin(pmin(1., p1), m2) if h >= 0. else pmin(pmin(1., m1), p2)
+                hl = ae * h
+                x = hl * out[v][0]
+                out[v][2] = out[v][2] - x if second else out[v][2] + x
+                if writer:
+                    g["adf_h_out"][ew + z] = hl
+        for v, (ar, dv, dh) in out.items():
+            o = s["grow"] + v
+            g["adf_v_out"][o] = fl[v]
+            g["del_ttf_advvert"][o] = dv
+            g["del_ttf_advhoriz"][o] = dh
+
+
+def unpad(a, P, width):
+    return a.reshape(-1, P)[:, :width]
+
+
+def compare(m, f, g, P, want, owned=None):
+    L = m.L
+    pairs = [("fct_ttf_max", "fct_ttf_max", L), ("fct_ttf_min", "fct_ttf_min", L), ("fct_plus", "fct_plus", L),
+             ("fct_minus", "fct_minus", L), ("adf_v_out", "fct_adf_v", m.nl), ("del_ttf_advvert", "del_ttf_advvert", L),
+             ("del_ttf_advhoriz", "del_ttf_advhoriz", L)]
+    for k, wk, w in pairs:
+        a, b = unpad(g[k], P, w), getattr(want, wk)
+        if owned is not None:
+            a, b = a[:owned], b[:owned]
+        assert bits_equal(a, b), k
+    if owned is None:
+        assert bits_equal(unpad(g["adf_h_out"], P, L), want.fct_adf_h)
+
+
+@pytest.mark.parametrize("name,nch,tn,cap", [("tiny", 1, 64, 74 * 1024), ("tiny", 2, 3, 74 * 1024),
+                                             ("pi", 1, 64, 74 * 1024), ("pi", 2, 24, 24 * 1024)])
+def test_tables_reproduce_the_oracle(mesh_mod, abi, oracle_mod, name, nch, tn, cap):
+    m = mesh_mod.make_workload(name)
+    f = mesh_mod.make_fields(m)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    st, nt, smem, blob, off = inspect(abi, m, tn, nch, cap)
+    assert st == 0 and nt >= 1 and smem <= cap
+    g, P = emulate(m, f, blob, off, nt, nch)
+    compare(m, f, g, P, want)
+
+
+def test_deep_columns_need_two_chunks(mesh_mod, abi):
+    m = mesh_mod.make_mesh(12, 9, 80, seed=3)
+    assert inspect(abi, m, 64, 1, 112 * 1024)[0] == 2        # 40 level pairs do not fit 32 lanes
+    st, nt, smem, blob, off = inspect(abi, m, 64, 2, 112 * 1024)
+    assert st == 0 and smem <= 112 * 1024
+
+
+def test_non_triangulation_is_refused(mesh_mod, abi):
+    m, _ = mesh_mod.adversarial_case(120, 17, seed=5)
+    assert inspect(abi, m)[0] == 2
+
+
+def test_partitioned_tables(mesh_mod, abi, oracle_mod):
+    """Boundary + interior tile sets of every partition, halo exchange emulated: owned results equal
+    the single-domain oracle (writer flags, halo rows as neighbours, cut edges)."""
+    m = mesh_mod.make_workload("tiny")
+    f = mesh_mod.make_fields(m)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    parts = mesh_mod.partition_mesh(m, 3)
+    lfs = [mesh_mod.slice_fields(f, p) for p in parts]
+    # phase A on every rank, exchange of fct_plus / fct_minus, phase B: run the emulator twice per
+    # rank (the second time with the exchanged factors) and keep phase B of the second run
+    gplus = np.array(f.fct_plus)
+    gminus = np.array(f.fct_minus)
+    runs = []
+    for p, lf in zip(parts, lfs):
+        tabs = [inspect(abi, p.mesh, 16, 1, 74 * 1024, which) for which in (1, 2)]
+        assert all(t[0] == 0 for t in tabs)
+        runs.append(tabs)
+        for st, nt, smem, blob, off in tabs:
+            g, P = emulate(p.mesh, lf, blob, off, nt, 1)
+            n = p.mesh.myDim_nod2D
+            own = np.zeros(p.mesh.nnod, bool)
+            # rows this tile set wrote = nodes whose fct_plus changed from the input
+            pl, mi = unpad(g["fct_plus"], P, m.L), unpad(g["fct_minus"], P, m.L)
+            ch = (pl != lf.fct_plus).any(1) | (mi != lf.fct_minus).any(1)
+            own[:n] = ch[:n]
+            gplus[p.mesh.node_gid[own]] = pl[own]
+            gminus[p.mesh.node_gid[own]] = mi[own]
+    assert bits_equal(gplus, want.fct_plus) and bits_equal(gminus, want.fct_minus)
