@@ -267,31 +267,24 @@ static void build_plan_tiles(Plan *p, const DerivedHost &d, const int *nlev_n)
 }
 
 // ---- warp-item kernels: plan tables, launch ---------------------------------------------------
-static const int WT_SMEM_MAX = 227 * 1024;
+static int wt_stages() { return std::min(std::max(env_int("FCT_WT_STAGES", 3), 2), 3); }
+// one stage of the ring: an equal share of the 227 KB a CTA may own
+static int wt_stage_cap(int stages) { return ((WT_SMEM_MAX - WT_SMEM_HEAD) / stages) & ~127; }
 
 static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
 {
     p->wtiles_ok = false;
     if (env_int("FCT_WTILE", 1) == 0) return;
     const int verbose = env_int("FCT_VERBOSE", 0);
-    const int slots = (p->nl - 1 + 1) / 2;   // level pairs of the deepest possible column
-    int nch = env_int("FCT_WT_NCH", 0);
-    if (nch <= 0) nch = slots > 32 ? 2 : 1;
-    if (nch > 2 || slots > 32 * nch) {
-        if (verbose) std::fprintf(stderr, "fesom2-accelerate: nl = %d does not fit a warp item: no warp-item tiles\n", p->nl);
-        return;
-    }
-    // default footprint: three CTAs per SM up to 48 levels, two beyond
-    const int cap_dflt = (p->nl <= 48 ? 74 : 112) * 1024;
     int cap = env_int("FCT_WT_SMEM", 0);   // 0: default
-    cap = cap <= 0 ? cap_dflt : std::min(std::max(cap, 8 * 1024), WT_SMEM_MAX);
+    cap = cap <= 0 ? wt_stage_cap(wt_stages()) : std::min(std::max(cap, 8 * 1024), wt_stage_cap(2));
     int TN = env_int("FCT_WT_NODES", 0);
-    TN = TN <= 0 ? 64 : std::min(TN, 255);
+    TN = TN <= 0 ? 96 : std::min(TN, 255);
     const std::vector<int> *lists[3] = {nullptr, &d.boundary, &d.interior};
     const int nsets = p->H > 0 ? 3 : 1;
     WarpTilesHost h[3];
     for (int s = 0; s < nsets; ++s) {
-        if (!build_warptiles(d, nlev_n, p->N, p->N + p->H, p->G, p->pitch, lists[s], TN, nch, cap, h[s])) {
+        if (!build_warptiles(d, nlev_n, p->N, p->N + p->H, p->G, p->pitch, lists[s], TN, cap, h[s])) {
             if (verbose) std::fprintf(stderr, "fesom2-accelerate: mesh is not eligible for the warp-item kernels\n");
             return;
         }
@@ -306,27 +299,29 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
         if (verbose && h[s].ntiles > 0)
             std::fprintf(stderr,
                          "fesom2-accelerate: warp tiles[%d]: %d tiles, %.1f nodes/tile, %.2f staged rows/node, %.2f staged edge rows/node "
-                         "(%.2f edge uses/node), lane fill %.1f%%, %.0f B plan/node, %d B smem, nch %d\n",
+                         "(%.2f edge uses/node), lane fill %.1f%%, %.0f B plan/node, %d B smem/stage\n",
                          s, h[s].ntiles, (double)h[s].nodes / h[s].ntiles, (double)h[s].staged_rows / h[s].nodes,
                          (double)h[s].staged_erows / h[s].nodes, (double)h[s].edge_uses / h[s].nodes,
                          100.0 * h[s].slots / std::max<long long>(h[s].lanes, 1), 16.0 * h[s].blob.size() / h[s].nodes,
-                         h[s].smem_bytes, nch);
+                         h[s].smem_bytes);
     }
-    p->wt_nch = nch;
     p->wtiles_ok = true;
 }
 
-typedef void (*warp_kern_t)(Arrays, WarpTilesDev);
+typedef void (*warp_kern_t)(Arrays, WarpTilesDev, int, int);
 struct WarpVariant {
     warp_kern_t fn;
-    const char *name;
+    bool phase_a;
+    int stages, consumers, issuers;
 };
-// [phase][nch - 1][minb - 1]
-static const WarpVariant g_wvariants[2][2][3] = {
-    {{{k_phaseA_warp<1, 1>, "A nch1 minb1"}, {k_phaseA_warp<1, 2>, "A nch1 minb2"}, {k_phaseA_warp<1, 3>, "A nch1 minb3"}},
-     {{k_phaseA_warp<2, 1>, "A nch2 minb1"}, {k_phaseA_warp<2, 2>, "A nch2 minb2"}, {k_phaseA_warp<2, 3>, "A nch2 minb3"}}},
-    {{{k_phaseB_warp<1, 1>, "B nch1 minb1"}, {k_phaseB_warp<1, 2>, "B nch1 minb2"}, {k_phaseB_warp<1, 3>, "B nch1 minb3"}},
-     {{k_phaseB_warp<2, 1>, "B nch2 minb1"}, {k_phaseB_warp<2, 2>, "B nch2 minb2"}, {k_phaseB_warp<2, 3>, "B nch2 minb3"}}},
+// total warps (1 fetcher + issuers + [converter] + consumers) a multiple of 4: see fct_warp_kernels.cuh
+#define WT_VA(S, C, I) {k_phase_warp<true, S, C, I>, true, S, C, I}
+#define WT_VB(S, C, I) {k_phase_warp<false, S, C, I>, false, S, C, I}
+static const WarpVariant g_wvariants[] = {
+    WT_VA(3, 18, 4), WT_VA(3, 14, 4), WT_VA(3, 16, 6), WT_VA(3, 10, 4), WT_VA(3, 20, 2),
+    WT_VA(2, 18, 4), WT_VA(2, 14, 4), WT_VA(2, 16, 6), WT_VA(2, 10, 4), WT_VA(2, 20, 2),
+    WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 13, 2), WT_VB(3, 19, 4), WT_VB(3, 13, 6),
+    WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(2, 13, 2), WT_VB(2, 19, 4), WT_VB(2, 13, 6),
 };
 
 // which: 0 all owned nodes, 1 boundary list, 2 interior list
@@ -339,26 +334,50 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");
         return false;
     }
-    const int ph = isA ? 0 : 1, ni = p->wt_nch - 1;
-    const size_t smem = (size_t)T.smem_bytes;
-    // resident CTAs the register allocation is bounded for: as many as the shared memory admits
-    const int fit = (int)std::min<size_t>(3, std::max<size_t>(1, (size_t)(228 * 1024) / (smem + 1024)));
-    int minb = env_int(isA ? "FCT_WT_MINB_A" : "FCT_WT_MINB_B", 0);   // 0: default
-    minb = minb <= 0 ? fit : std::min(minb, 3);
-    const WarpVariant &v = g_wvariants[ph][ni][minb - 1];
-    static size_t attr_set[2][2][3] = {};
-    if (smem > attr_set[ph][ni][minb - 1]) {
-        if (!cuda_ok(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute"))
-            return false;
-        attr_set[ph][ni][minb - 1] = smem;
-        if (env_int("FCT_VERBOSE", 0)) {
-            int per_sm = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, WT_THREADS, smem);
-            std::fprintf(stderr, "fesom2-accelerate: warp kernel %s: %zu B smem, %d CTAs/SM\n", v.name, smem, per_sm);
+    const int stage_bytes = (T.smem_bytes + 127) & ~127;
+    // as deep a ring as the tiles of this plan admit
+    int stages = wt_stages();
+    while (stages > 2 && WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) --stages;
+    if (WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) {
+        std::fprintf(stderr, "fesom2-accelerate: warp tiles of %d B do not fit two stages\n", stage_bytes);
+        return false;
+    }
+    // consumer / issuer warps: the closest compiled variant (0: default)
+    int nwc = env_int(isA ? "FCT_WT_WARPS_A" : "FCT_WT_WARPS_B", 0), npw = env_int("FCT_WT_ISSUERS", 0);
+    nwc = nwc <= 0 ? (isA ? 18 : 15) : nwc;
+    npw = npw <= 0 ? 4 : npw;
+    constexpr int NV = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
+    int vi = -1, best = 1 << 30;
+    for (int i = 0; i < NV; ++i) {
+        if (g_wvariants[i].stages != stages || g_wvariants[i].phase_a != isA) continue;
+        const int dist = 4 * std::abs(g_wvariants[i].consumers - nwc) + std::abs(g_wvariants[i].issuers - npw);
+        if (dist < best) {
+            best = dist;
+            vi = i;
         }
     }
-    dim3 grid(T.ntiles, ntracers, 1);
-    v.fn<<<grid, WT_THREADS, smem, s>>>(A, T);
+    const int ph = isA ? 0 : 1;
+    const WarpVariant &v = g_wvariants[vi];
+    const size_t smem = WT_SMEM_HEAD + (size_t)stages * stage_bytes;
+    static size_t attr_set[2][NV] = {};
+    if (smem > attr_set[ph][vi]) {
+        if (!cuda_ok(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute"))
+            return false;
+        attr_set[ph][vi] = smem;
+        if (env_int("FCT_VERBOSE", 0))
+            std::fprintf(stderr, "fesom2-accelerate: warp kernel %c: %d stages of %d B, %d consumer + %d issuer warps\n",
+                         isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers);
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+        sms = std::max(sms, 1);
+    }
+    const long long total = (long long)T.ntiles * ntracers;
+    dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
+    v.fn<<<grid, (v.issuers + 1 + (isA ? 1 : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");
 }

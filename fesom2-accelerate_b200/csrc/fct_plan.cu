@@ -203,11 +203,42 @@ inline int pad16(int b) { return (b + 15) & ~15; }
 inline int row_bytes(int levels) { return ((std::max(levels, 0) + 1) & ~1) * 8; }
 }   // namespace
 
+// Append the level-pair slots of tile-local node `ln` to a warp-item schedule of `len` lanes.  A
+// column that does not fit the rest of the current item is cut, with a ghost slot on either side
+// of the cut (phase A's stencil needs the neighbouring cluster bound); a cut is only made when at
+// least two real slots fit in front of it.  `v` may be null (dry run for the footprint).
+static void schedule_node(std::vector<unsigned short> *v, size_t &len, int ln, int s)
+{
+    auto put = [&](unsigned short d) {
+        if (v) v->push_back(d);
+        ++len;
+    };
+    int i = 0;
+    while (i < s) {
+        const int fill = (int)(len % 32);
+        const int room = 32 - fill;
+        const int lead = i > 0 ? 1 : 0;   // continuing a cut column: ghost of slot i-1 first
+        if (s - i + lead <= room) {
+            if (lead) put((unsigned short)(ln | ((i - 1) << 8) | 0x8000));
+            for (; i < s; ++i) put((unsigned short)(ln | (i << 8)));
+            break;
+        }
+        const int real = room - lead - 1;   // slots in front of the trailing ghost
+        if (real < 2) {
+            for (int k = 0; k < room; ++k) put((unsigned short)WT_IDLE);
+            continue;
+        }
+        if (lead) put((unsigned short)(ln | ((i - 1) << 8) | 0x8000));
+        for (int k = 0; k < real; ++k, ++i) put((unsigned short)(ln | (i << 8)));
+        put((unsigned short)(ln | (i << 8) | 0x8000));
+    }
+}
+
 bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P,
-                     const std::vector<int> *list, int TN, int nch, int smem_cap, WarpTilesHost &out)
+                     const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out)
 {
     const int count = list ? (int)list->size() : N;
-    const int W = 32 * nch;
+    const int W = 32;
     out = WarpTilesHost();
     out.blob_off.assign(1, 0u);
     if (P > 256 || (P & 1) || TN < 1 || TN > 255) return false;
@@ -222,7 +253,7 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
     std::vector<char> checked((size_t)N, 0);
 
     auto need_bytes = [&](size_t nrows, size_t nerows, size_t nn, size_t nent, size_t nsched, int rb, int eb) {
-        const size_t blob = WT_HDR_BYTES + pad16((int)nrows * 8) + pad16((int)nerows * 8) + nn * 16 + nent * 16 +
+        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + nn * 16 + nent * 16 +
                             pad16((int)((nsched + W - 1) / W * W) * 2);
         return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack;
     };
@@ -284,10 +315,8 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
                 }
             }
             const int s = (nz + 1) / 2;
-            if (s > W) return false;
             size_t nsched = sched.size();
-            if (s > 0 && (int)(nsched % W) + s > W) nsched = (nsched + W - 1) / W * W;
-            nsched += s;
+            schedule_node(nullptr, nsched, nn, s);
             const size_t need = need_bytes(rows.size() + add_rows, erows.size() + add_erows, nn + 1, ent.size() + cnt,
                                            nsched, rb + add_rb, eb + add_eb);
             if ((int)need > smem_cap || ent.size() + cnt > 65535) {
@@ -322,8 +351,10 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
                                       (FCT_META_SECOND(e.z) ? 0x80000000u : 0u);
                 ent.push_back(make_int4(esoff[e.x], other, (int)meta, (int)((long long)e.x * P)));
             }
-            if (s > 0 && (int)(sched.size() % W) + s > W) sched.resize((sched.size() + W - 1) / W * W, (unsigned short)WT_IDLE);
-            for (int i = 0; i < s; ++i) sched.push_back((unsigned short)(nn | (i << 8)));
+            {
+                size_t len = sched.size();
+                schedule_node(&sched, len, nn, s);
+            }
             out.slots += s;
             out.edge_uses += cnt;
             ++nn;
@@ -332,22 +363,22 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         sched.resize((sched.size() + W - 1) / W * W, (unsigned short)WT_IDLE);
         // ---- assemble the blob ----
         const int off_rows = WT_HDR_BYTES;
-        const int off_erows = off_rows + pad16((int)rows.size() * 8);
-        const int off_hdr = off_erows + pad16((int)erows.size() * 8);
+        const int n_copies = 2 * (int)rows.size() + (int)erows.size();
+        const int off_hdr = off_rows + pad16(n_copies * 8);
         const int off_ent = off_hdr + (int)hdr.size() * 16;
         const int off_sched = off_ent + (int)ent.size() * 16;
         const int blob_bytes = off_sched + pad16((int)sched.size() * 2);
         long long tx = 0;
         for (auto &r : rows) tx += 2LL * r.bytes;
         for (auto &r : erows) tx += r.bytes;
-        if (tx >= (1 << 20)) return false;   // mbarrier transaction-count range
+        if (tx >= (1 << 20) || 2 * rb + eb >= (1 << 20)) return false;   // mbarrier transaction-count range, 16-bit offsets
         std::vector<unsigned char> buf((size_t)blob_bytes, 0);
         int *h = reinterpret_cast<int *>(buf.data());
-        h[0] = (int)rows.size();
+        h[0] = n_copies;
         h[1] = (int)erows.size();
         h[2] = nn;
         h[3] = (int)sched.size() / W;
-        h[4] = off_erows;
+        h[4] = (int)rows.size();
         h[5] = off_hdr;
         h[6] = off_ent;
         h[7] = off_sched;
@@ -355,12 +386,24 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         h[9] = rb;
         h[10] = eb;
         h[11] = (int)tx;
-        auto put_rows = [&](const std::vector<StagedRow> &v, int off) {
-            int2 *t = reinterpret_cast<int2 *>(buf.data() + off);
-            for (size_t i = 0; i < v.size(); ++i) t[i] = make_int2((int)v[i].goff, (v[i].soff >> 4) | ((v[i].bytes >> 4) << 16));
-        };
-        put_rows(rows, off_rows);
-        put_rows(erows, off_erows);
+        {
+            // copy list: the rows of the three regions interleaved, so that the issuer warps (which
+            // take consecutive 32-entry chunks) all touch every array; zero-length rows are dropped
+            int2 *t = reinterpret_cast<int2 *>(buf.data() + off_rows);
+            int k = 0;
+            auto put = [&](const StagedRow &r, int region_off, int arr) {
+                if (r.bytes > 0) t[k++] = make_int2((int)r.goff, ((r.soff + region_off) >> 4) | ((r.bytes >> 4) << 16) | (arr << 24));
+            };
+            const size_t nmax = std::max(rows.size(), erows.size());
+            for (size_t i = 0; i < nmax; ++i) {
+                if (i < rows.size()) {
+                    put(rows[i], 0, 0);
+                    put(rows[i], rb, 1);
+                }
+                if (i < erows.size()) put(erows[i], 2 * rb, 2);
+            }
+            h[0] = k;
+        }
         if (!hdr.empty()) std::memcpy(buf.data() + off_hdr, hdr.data(), hdr.size() * 16);
         if (!ent.empty()) std::memcpy(buf.data() + off_ent, ent.data(), ent.size() * 16);
         if (!sched.empty()) std::memcpy(buf.data() + off_sched, sched.data(), sched.size() * 2);
@@ -387,7 +430,7 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
 extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D, int *myDim_edge2D,
                                       int *nl, int *nlevels_nod2D, int *nlevels_elem2D, int *elem2D_nodes,
                                       int *nod_in_elem2D_num, int *nod_in_elem2D, int *nod_in_elem2D_dim,
-                                      int *edges, int *edge_tri, int *tile_nodes, int *nch, int *smem_cap,
+                                      int *edges, int *edge_tri, int *tile_nodes, int *smem_cap,
                                       int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
                                       unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat)
 {
@@ -403,7 +446,7 @@ extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *my
     const std::vector<int> *list = *which == 1 ? &d.boundary : (*which == 2 ? &d.interior : nullptr);
     WarpTilesHost h;
     const int P = (*nl + 1) & ~1;
-    if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, list, *tile_nodes, *nch, *smem_cap, h)) {
+    if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, list, *tile_nodes, *smem_cap, h)) {
         *istat = 2;   // mesh not eligible
         return;
     }

@@ -52,12 +52,12 @@ struct WarpTilesHost {
 };
 // Greedy tiling of `list` (nullptr: the identity 0..N-1): a tile closes after TN nodes or when its
 // shared-memory footprint (blob + two staged node-row regions + the edge-row region) would exceed
-// smem_cap.  `nch`: virtual-lane chunks per lane (a warp item has 32*nch slots of two levels).
+// smem_cap (the size of one stage of the kernels' ring).
 // Returns false when the mesh is not a plain triangulation (ring neighbours == edge neighbours
-// with equal depths, every edge at most as deep as both of its end nodes), a column does not fit
-// a warp item or an offset does not fit its field: the caller then keeps the other kernels.
+// with equal depths, every edge at most as deep as both of its end nodes) or an offset does not
+// fit its field: the caller then keeps the other kernels.
 bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P,
-                     const std::vector<int> *list, int TN, int nch, int smem_cap, WarpTilesHost &out);
+                     const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out);
 
 struct Plan {
     unsigned magic = 0x504c414eu;
@@ -72,7 +72,6 @@ struct Plan {
     bool tiles_ok = false;
     // warp-item kernels: one tile set serves both phases; [0 all owned, 1 boundary, 2 interior]
     WarpTilesDev wtiles[3] = {};
-    int wt_nch = 1;
     bool wtiles_ok = false;
     std::vector<void *> owned;   // device allocations to free
 };

@@ -1,27 +1,36 @@
-// Warp-item fused kernels with TMA-staged tiles: the fast path of the device-resident step.
+// Persistent, warp-specialised fused kernels with TMA-staged tiles: the fast path of the
+// device-resident step.
 //
 // The tile-staged kernels of fct_tile_kernels.cuh turned out to be bound by instruction issue
 // (profiles/r1_v1_*: 123 M + 99 M warp instructions per CORE2 step, a quarter of them index
-// arithmetic, DRAM traffic only 1.2x algorithmic).  Here every irregular decision is taken by the
-// inspector (fct_plan.cu, build_warptiles) and the kernels only stream:
+// arithmetic, DRAM traffic only 1.2x algorithmic), and a first CTA-per-tile TMA version spent 43 %
+// of its warp time waiting for its own staging (profiles/r1_v2_*).  Here every irregular decision
+// is taken by the inspector (fct_plan.cu, build_warptiles), the kernels only stream, and staging
+// runs ahead of the arithmetic:
 //
 //   * A tile is a run of consecutive owned nodes.  Its plan data is ONE contiguous blob: header,
 //     table of node rows to stage, table of edge-flux rows to stage, one header per node, the
 //     nodes' edge entries with precomputed shared-memory BYTE offsets, and a warp-item schedule.
-//   * Staging is done by the TMA unit: thread 0 bulk-copies the blob (cp.async.bulk, SASS UBLKCP)
-//     against mbarrier 0; the lanes of warp 0 then issue one bulk copy per row -- exactly the
-//     active levels, in 16-byte granules -- for the two gathered node arrays (phase A: fct_LO and
-//     ttf, converted in place to the a1 bounds of reference.cpp:315-316; phase B: fct_plus and
-//     fct_minus) and for the edge-flux rows of the tile, against mbarrier 1.  Every edge whose two
-//     end nodes lie in the tile is fetched once instead of once per end node.
-//   * A warp item is 32*NCH virtual lanes, each a (node, pair of ACTIVE levels) slot; slots of a
-//     node are consecutive virtual lanes and never straddle an item, so the vertical 3-point
-//     stencil of a3 is done with warp shuffles and warps never meet at a CTA barrier after the
-//     staging.  Lane l holds virtual lanes l, l+32, ... (NCH independent chains for ILP; a column
-//     may have up to 64*NCH levels).
+//   * One persistent CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through an
+//     NSTAGE-deep ring of shared-memory stages guarded by mbarriers.  Producer warps feed the ring
+//     with the TMA unit (cp.async.bulk, SASS UBLKCP): warp 0 fetches the blob; NPW issuer warps
+//     share the tile's copy list -- one bulk copy per staged row, exactly the active levels in
+//     16-byte granules: the node rows of the two gathered arrays (phase A: fct_LO and ttf; phase
+//     B: fct_plus and fct_minus) and the edge-flux rows (every edge with both ends in the tile is
+//     fetched once, not once per end) -- a single warp cannot issue them fast enough
+//     (profiles/r1_v3_*); in phase A one more warp turns the landed (fct_LO, ttf) rows in place
+//     into the a1 bounds of reference.cpp:315-316.  NWC consumer warps pull warp items of the
+//     ready stage from a shared counter, so tiles k+1 and k+2 are in flight while tile k is
+//     computed, and each consumer loads the first-needed own-column values of its NEXT item while
+//     it works on the current one.
+//   * A warp item is 32 lanes, each a (node, pair of ACTIVE levels) slot; consecutive lanes hold
+//     consecutive slots of a node, so the vertical 3-point stencil of a3 is two warp shuffles.  A
+//     column that does not fit the rest of an item is split, with one GHOST slot on either side of
+//     the cut (it recomputes the neighbouring cluster bound and stores nothing), which keeps the
+//     lanes > 90 % full at any depth.
 //   * In the item loop every shared-memory address is "region base + precomputed offset + 8*z0",
-//     level masks ride on the DSETP...AND predicates, and the +/- split of b1 horizontal is two
-//     predicated DADDs (adding +0 is exact, and the sums never are -0).
+//     level masks ride on the DSETP...AND predicates, the +/- split of b1 horizontal is a
+//     predicated sum (adding +0 is exact, and the sums never are -0).
 //
 // Arithmetic and its order are those of fct_kernels.cuh (bit-identical results).
 #pragma once
@@ -38,12 +47,15 @@ struct WarpTilesDev {
     int smem_bytes;             // dynamic shared memory of one CTA (max over tiles)
 };
 
-constexpr int WT_THREADS = 256;
-constexpr int WT_WARPS = WT_THREADS / 32;
+// warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A NPW+1 the a1 converter, then NWC consumers
+// (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128, 20 -> 96, 24 -> 80)
+constexpr int WT_SMEM_HEAD = 128;     // mbarriers + item counters in front of the stages
+constexpr int WT_SMEM_MAX = 227 * 1024;
 // blob header: 16 ints
 //  [0] node rows  [1] edge rows  [2] nodes  [3] warp items
 //  [4] byte offset of the edge-row table  [5] of the node headers  [6] of the entries  [7] of the schedule
 //  [8] blob bytes  [9] bytes of ONE staged node-row region  [10] bytes of the edge-row region  [11] bytes the row copies deliver
+// schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
 // node-row table at byte 64: int2 {global element offset of the row, (16-byte units) smem offset | size << 16}
 // node header int4: {node*pitch, nz | fillmin << 8 | self depth << 16, smem byte offset of the own row, first entry | entries << 16}
 // entry int4: {smem byte offset of the edge row, smem byte offset of the other node's row,
@@ -63,6 +75,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void fence_mbar_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -234,395 +254,396 @@ __device__ __forceinline__ void wt_edge_b(int z0, int meta, const double2 &po, c
 }
 
 struct WtView {
-    int n_rows, n_erows, n_nodes, n_witems;
+    int n_copies, n_nodes, n_witems;
     unsigned char *blob, *rowsA, *rowsB, *erows;
     const int4 *hdr, *ent;
     const unsigned short *sched;
-    int rows_bytes;
+    int rows_bytes, erows_bytes, tx_bytes;
+    const int2 *copies;
 };
 
-// Load the tile's blob and stage its rows.  src_a / src_b: the two gathered node arrays of this
-// tracer, src_e: the edge fluxes.  Returns after the rows have landed (all threads).
-__device__ __forceinline__ WtView wt_stage(unsigned char *sm, const WarpTilesDev &T, const double *src_a,
-                                           const double *src_b, const double *src_e)
+__device__ __forceinline__ WtView wt_view(unsigned char *stage)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned b0 = __ldg(T.blob_off + blockIdx.x), b1 = __ldg(T.blob_off + blockIdx.x + 1);
-    const uint32_t bar0 = smem_u32(sm), bar1 = bar0 + 8;
     WtView v;
-    v.blob = sm + 16;
-    if (tid == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar1, 1);
-        fence_mbar_init();
-        mbar_expect_tx(bar0, (b1 - b0) * 16u);
-        bulk_g2s(smem_u32(v.blob), T.blob + b0, (b1 - b0) * 16u, bar0);
-    }
-    __syncthreads();
-    mbar_wait(bar0, 0);
-    const int4 h0 = reinterpret_cast<const int4 *>(v.blob)[0];
-    const int4 h1 = reinterpret_cast<const int4 *>(v.blob)[1];
-    const int4 h2 = reinterpret_cast<const int4 *>(v.blob)[2];
-    v.n_rows = h0.x;
-    v.n_erows = h0.y;
+    v.blob = stage;
+    const int4 h0 = reinterpret_cast<const int4 *>(stage)[0];
+    const int4 h1 = reinterpret_cast<const int4 *>(stage)[1];
+    const int4 h2 = reinterpret_cast<const int4 *>(stage)[2];
+    v.n_copies = h0.x;
     v.n_nodes = h0.z;
     v.n_witems = h0.w;
     v.rows_bytes = h2.y;
-    v.rowsA = v.blob + h2.x;
+    v.erows_bytes = h2.z;
+    v.tx_bytes = h2.w;
+    v.rowsA = stage + h2.x;
     v.rowsB = v.rowsA + h2.y;
     v.erows = v.rowsB + h2.y;
-    v.hdr = reinterpret_cast<const int4 *>(v.blob + h1.y);
-    v.ent = reinterpret_cast<const int4 *>(v.blob + h1.z);
-    v.sched = reinterpret_cast<const unsigned short *>(v.blob + h1.w);
-    if (warp == 0) {
-        if (lane == 0) mbar_expect_tx(bar1, (uint32_t)h2.w);
-        __syncwarp();
-        const uint32_t sa = smem_u32(v.rowsA), sb = smem_u32(v.rowsB), se = smem_u32(v.erows);
-        const int2 *rt = reinterpret_cast<const int2 *>(v.blob + WT_HDR_BYTES);
-        for (int u = lane; u < v.n_rows; u += 32) {
-            const int2 r = rt[u];
-            const uint32_t so = ((uint32_t)r.y & 0xffffu) << 4, sz = ((uint32_t)r.y >> 16) << 4;
-            if (sz) {
-                bulk_g2s(sa + so, src_a + (uint32_t)r.x, sz, bar1);
-                bulk_g2s(sb + so, src_b + (uint32_t)r.x, sz, bar1);
-            }
-        }
-        const int2 *et = reinterpret_cast<const int2 *>(v.blob + h1.x);
-        for (int u = lane; u < v.n_erows; u += 32) {
-            const int2 r = et[u];
-            const uint32_t so = ((uint32_t)r.y & 0xffffu) << 4, sz = ((uint32_t)r.y >> 16) << 4;
-            if (sz) bulk_g2s(se + so, src_e + (uint32_t)r.x, sz, bar1);
-        }
-    }
-    mbar_wait(bar1, 0);
+    v.copies = reinterpret_cast<const int2 *>(stage + WT_HDR_BYTES);
+    v.hdr = reinterpret_cast<const int4 *>(stage + h1.y);
+    v.ent = reinterpret_cast<const int4 *>(stage + h1.z);
+    v.sched = reinterpret_cast<const unsigned short *>(stage + h1.w);
     return v;
 }
 
-// previous / next virtual lane's value (virtual lane = chunk*32 + lane)
-template <int NCH>
-__device__ __forceinline__ void vl_neighbours(const double (&lo_end)[NCH], const double (&hi_end)[NCH], int lane,
-                                              double (&prev)[NCH], double (&next)[NCH])
+struct WtItem {
+    bool act, out;   // lane holds a slot; the slot stores results (not a ghost)
+    int z0, nz, cnt, fm, sd, own;
+    unsigned grow;   // element offset of (node, z0) in the padded node arrays
+    const int4 *en;
+    const unsigned char *ra, *rb, *re;
+};
+
+__device__ __forceinline__ WtItem wt_item(const WtView &V, int wi, int lane)
 {
-    // lo_end[c]: this virtual lane's value at its FIRST level, hi_end[c]: at its SECOND level
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        prev[c] = __shfl_up_sync(0xffffffffu, hi_end[c], 1);
-        next[c] = __shfl_down_sync(0xffffffffu, lo_end[c], 1);
+    WtItem I;
+    const unsigned d = V.sched[wi * 32 + lane];
+    I.act = d != WT_IDLE;
+    I.out = I.act && !(d & 0x8000u);
+    const int4 hd = V.hdr[I.act ? (d & 0xffu) : 0u];
+    I.z0 = I.act ? (int)((d >> 8) & 0x7fu) * 2 : 0;
+    I.nz = I.act ? (hd.y & 0xff) : 0;
+    I.cnt = I.act ? (int)((unsigned)hd.w >> 16) : 0;
+    I.fm = (hd.y >> 8) & 0xff;
+    I.sd = (hd.y >> 16) & 0xff;
+    I.own = hd.z;
+    I.grow = (unsigned)hd.x + (unsigned)I.z0;
+    I.en = V.ent + (hd.w & 0xffff);
+    I.ra = V.rowsA + I.z0 * 8;
+    I.rb = V.rowsB + I.z0 * 8;
+    I.re = V.erows + I.z0 * 8;
+    return I;
+}
+
+// The own-column values an item needs FIRST (everything else it loads has the whole edge loop to
+// arrive): the raw vertical fluxes of levels z0 .. z0+2 and, in phase B, the cell areas.  Loaded
+// one item ahead.
+struct WtEarly {
+    double f0, f1, f2, a0, a1;
+};
+template <bool PHASE_A>
+__device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, int wi, int lane, const double *g_v)
+{
+    WtEarly E;
+    E.f0 = E.f1 = E.f2 = 0.;
+    E.a0 = E.a1 = 1.;
+    const unsigned d = V.sched[wi * 32 + lane];
+    if (d != WT_IDLE && !(d & 0x8000u)) {
+        const int4 hd = V.hdr[d & 0xffu];
+        const int z0 = (int)((d >> 8) & 0x7fu) * 2, nz = hd.y & 0xff;
+        const unsigned grow = (unsigned)hd.x + (unsigned)z0;
+        const double2 ff = __ldg(reinterpret_cast<const double2 *>(g_v + grow));
+        if (z0 + 2 <= nz) E.f2 = __ldg(g_v + grow + 2);
+        E.f0 = ff.x;
+        E.f1 = ff.y;
+        if (!PHASE_A) {
+            const double2 aa = __ldg(reinterpret_cast<const double2 *>(A.area + grow));
+            E.a0 = aa.x;
+            E.a1 = aa.y;
+        }
     }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        if (c > 0) {
-            const double w = __shfl_sync(0xffffffffu, hi_end[c - 1], 31);
-            if (lane == 0) prev[c] = w;
+    return E;
+}
+
+// ---- phase A: one warp item ------------------------------------------------------------------------
+__device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
+                                          const double *g_lo, const WtEarly &E)
+{
+    const WtItem I = wt_item(V, wi, lane);
+    const int z0 = I.z0, nz = I.nz;
+    double hi0, hi1, lw0, lw1, p0, p1, m0, m1, l0 = 0., l1 = 0., ai0 = 0., ai1 = 0.;
+    {
+        // own column: needed after the gather only
+        if (I.out) {
+            const double2 ll = __ldg(reinterpret_cast<const double2 *>(g_lo + I.grow));
+            const double2 aa = __ldg(reinterpret_cast<const double2 *>(A.area_inv + I.grow));
+            l0 = ll.x; l1 = ll.y;
+            ai0 = aa.x; ai1 = aa.y;
         }
-        if (c + 1 < NCH) {
-            const double w = __shfl_sync(0xffffffffu, lo_end[c + 1], 0);
-            if (lane == 31) next[c] = w;
+        // cluster bounds start from the (-big, +big) fill of ring elements that already ended
+        // (reference.cpp:341-349) and the node's own a1 bounds
+        const bool fl0 = z0 >= I.fm, fl1 = z0 + 1 >= I.fm;
+        hi0 = fl0 ? -A.big : -CUDART_INF;
+        lw0 = fl0 ? A.big : CUDART_INF;
+        hi1 = fl1 ? -A.big : -CUDART_INF;
+        lw1 = fl1 ? A.big : CUDART_INF;
+        const double2 x = *reinterpret_cast<const double2 *>(I.ra + I.own);
+        const double2 y = *reinterpret_cast<const double2 *>(I.rb + I.own);
+        if (I.act && z0 < I.sd) {
+            hi0 = pick_max(hi0, x.x);
+            lw0 = pick_min(lw0, y.x);
         }
+        if (I.act && z0 + 1 < I.sd) {
+            hi1 = pick_max(hi1, x.y);
+            lw1 = pick_min(lw1, y.y);
+        }
+        wt_b1v(E.f0, E.f1, E.f2, p0, p1, m0, m1);
+    }
+    // ---- the node's edges in ascending edge id: a2/a3 bounds + b1 horizontal ----
+#pragma unroll 2
+    for (int k = 0; k < I.cnt; ++k) {
+        const int4 e = I.en[k];
+        const double2 x = *reinterpret_cast<const double2 *>(I.ra + e.y);
+        const double2 y = *reinterpret_cast<const double2 *>(I.rb + e.y);
+        const double2 h = *reinterpret_cast<const double2 *>(I.re + e.x);
+        wt_edge_a(z0, e.z, x, y, h, hi0, hi1, lw0, lw1, p0, p1, m0, m1);
+    }
+    // ---- vertical 3-point stencil of a3 (reference.cpp:380-392): neighbouring slots are the
+    // neighbouring lanes (ghost slots included) ----
+    const double pmax = __shfl_up_sync(0xffffffffu, hi1, 1), pmin = __shfl_up_sync(0xffffffffu, lw1, 1);
+    const double nmax = __shfl_down_sync(0xffffffffu, hi0, 1), nmin = __shfl_down_sync(0xffffffffu, lw0, 1);
+    if (!I.out) return;
+    double bm0 = hi0, bn0 = lw0, bm1 = hi1, bn1 = lw1;
+    if (z0 > 0 && z0 < nz - 1) {
+        bm0 = pick_max(pick_max(pmax, hi0), hi1);
+        bn0 = pick_min(pick_min(pmin, lw0), lw1);
+    }
+    if (z0 + 1 < nz - 1) {
+        bm1 = pick_max(pick_max(hi0, hi1), nmax);
+        bn1 = pick_min(pick_min(lw0, lw1), nmin);
+    }
+    bm0 -= l0;
+    bn0 -= l0;
+    bm1 -= l1;
+    bn1 -= l1;
+    // ---- b2, reference.cpp:432-435 ----
+    double flux = p0 * A.dt * ai0 + A.eps;
+    const double pf0 = pick_min(1., div_exact(bm0, flux));
+    flux = m0 * A.dt * ai0 - A.eps;
+    const double mf0 = pick_min(1., div_exact(bn0, flux));
+    flux = p1 * A.dt * ai1 + A.eps;
+    const double pf1 = pick_min(1., div_exact(bm1, flux));
+    flux = m1 * A.dt * ai1 - A.eps;
+    const double mf1 = pick_min(1., div_exact(bn1, flux));
+    const size_t off = tn + I.grow;
+    if (z0 + 1 < nz) {
+        *reinterpret_cast<double2 *>(A.ttf_max + off) = make_double2(bm0, bm1);
+        *reinterpret_cast<double2 *>(A.ttf_min + off) = make_double2(bn0, bn1);
+        *reinterpret_cast<double2 *>(A.plus + off) = make_double2(pf0, pf1);
+        *reinterpret_cast<double2 *>(A.minus + off) = make_double2(mf0, mf1);
+    } else {
+        A.ttf_max[off] = bm0;
+        A.ttf_min[off] = bn0;
+        A.plus[off] = pf0;
+        A.minus[off] = mf0;
+    }
+}
+
+// ---- phase B: one warp item ------------------------------------------------------------------------
+__device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
+                                          double *g_vout, double *g_ho, const WtEarly &E)
+{
+    const WtItem I = wt_item(V, wi, lane);
+    if (!I.out) return;   // ghost slots exist for phase A's stencil only
+    const int z0 = I.z0, nz = I.nz;
+    const size_t off = tn + I.grow;
+    // ---- the own column's loads for c vertical: used after the edge loop ----
+    const double2 q_dv = *reinterpret_cast<const double2 *>(A.del_v + off);
+    const double2 q_dh = *reinterpret_cast<const double2 *>(A.del_h + off);
+    const double2 q_t = __ldg(reinterpret_cast<const double2 *>(A.ttf + off));
+    const double2 q_l = __ldg(reinterpret_cast<const double2 *>(A.lo + off));
+    const double2 q_hn = __ldg(reinterpret_cast<const double2 *>(A.hnode + I.grow));
+    const double2 q_hw = __ldg(reinterpret_cast<const double2 *>(A.hnode_new + I.grow));
+    // own factors from the staged rows: levels z0-1 .. z0+2
+    const unsigned char *pr = I.ra + I.own, *mr = I.rb + I.own;
+    const double2 pp = *reinterpret_cast<const double2 *>(pr);
+    const double2 mm = *reinterpret_cast<const double2 *>(mr);
+    const double p_m1 = *reinterpret_cast<const double *>(pr - 8);
+    const double m_m1 = *reinterpret_cast<const double *>(mr - 8);
+    const double p_p2 = *reinterpret_cast<const double *>(pr + 16);
+    const double m_p2 = *reinterpret_cast<const double *>(mr + 16);
+    // ---- b3 vertical, docs/refactoring.md:205-231 (the bottom flux stays) ----
+    double fl0, fl1, fl2;
+    {
+        double ae = 1.;
+        if (z0 == 0) {
+            ae = pick_min(ae, (E.f0 >= 0.) ? pp.x : mm.x);
+        } else if (E.f0 >= 0.) {
+            ae = pick_min(ae, m_m1);
+            ae = pick_min(ae, pp.x);
+        } else {
+            ae = pick_min(ae, p_m1);
+            ae = pick_min(ae, mm.x);
+        }
+        fl0 = ae * E.f0;
+    }
+    if (z0 + 1 < nz) {
+        double ae = 1.;
+        if (E.f1 >= 0.) {
+            ae = pick_min(ae, mm.x);
+            ae = pick_min(ae, pp.y);
+        } else {
+            ae = pick_min(ae, pp.x);
+            ae = pick_min(ae, mm.y);
+        }
+        fl1 = ae * E.f1;
+    } else {
+        fl1 = E.f1;
+    }
+    if (z0 + 2 < nz) {
+        double ae = 1.;
+        if (E.f2 >= 0.) {
+            ae = pick_min(ae, mm.y);
+            ae = pick_min(ae, p_p2);
+        } else {
+            ae = pick_min(ae, pp.y);
+            ae = pick_min(ae, m_p2);
+        }
+        fl2 = ae * E.f2;
+    } else {
+        fl2 = E.f2;
+    }
+    const double ar0 = A.dt / E.a0, ar1 = A.dt / E.a1;
+    double dh0 = q_dh.x, dh1 = q_dh.y;
+    // ---- b3 horizontal + c horizontal over the node's edges, ascending edge id ----
+#pragma unroll 2
+    for (int k = 0; k < I.cnt; ++k) {
+        const int4 e = I.en[k];
+        const double2 po = *reinterpret_cast<const double2 *>(I.ra + e.y);
+        const double2 mo = *reinterpret_cast<const double2 *>(I.rb + e.y);
+        const double2 h = *reinterpret_cast<const double2 *>(I.re + e.x);
+        double hl0, hl1;
+        wt_edge_b(z0, e.z, po, mo, h, pp.x, pp.y, mm.x, mm.y, ar0, ar1, dh0, dh1, hl0, hl1);
+        const int dg = e.z & 0xffff;
+        if ((e.z & 0x40000000) && z0 < dg) {
+            double *o = g_ho + (unsigned)e.w + z0;
+            if (z0 + 1 < dg) *reinterpret_cast<double2 *>(o) = make_double2(hl0, hl1);
+            else o[0] = hl0;
+        }
+    }
+    // ---- c vertical, docs/refactoring.md:295-300 ----
+    const double dv0 = q_dv.x - q_t.x * q_hn.x + q_l.x * q_hw.x + (fl0 - fl1) * ar0;
+    const double dv1 = q_dv.y - q_t.y * q_hn.y + q_l.y * q_hw.y + (fl1 - fl2) * ar1;
+    if (z0 + 1 < nz) {
+        *reinterpret_cast<double2 *>(g_vout + I.grow) = make_double2(fl0, fl1);
+        *reinterpret_cast<double2 *>(A.del_v + off) = make_double2(dv0, dv1);
+        *reinterpret_cast<double2 *>(A.del_h + off) = make_double2(dh0, dh1);
+    } else {
+        g_vout[I.grow] = fl0;
+        A.del_v[off] = dv0;
+        A.del_h[off] = dh0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Phase A = a1 + a2 + a3 + b1 vertical + b1 horizontal + b2
+// The persistent kernel.  PHASE_A: a1 + a2 + a3 + b1 vertical + b1 horizontal + b2;
+// else: b3 vertical + b3 horizontal + c vertical + c horizontal.
+// dynamic smem: WT_SMEM_HEAD + NSTAGE * stage_bytes
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int MINB>
-__global__ void __launch_bounds__(WT_THREADS, MINB) k_phaseA_warp(Arrays A, WarpTilesDev T)
+template <bool PHASE_A, int NSTAGE, int NWC, int NPW>
+__global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? 1 : 0) + NWC) * 32, 1)
+k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes)
 {
     extern __shared__ __align__(128) unsigned char wt_sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t tn = blockIdx.y * A.ts_node;
-    const WtView V = wt_stage(wt_sm, T, A.lo + tn, A.ttf + tn, A.adf_h_in + blockIdx.y * A.ts_edge);
-
-    // a1 in place on the staged rows: (fct_LO, ttf) -> (max, min), reference.cpp:315-316
-    {
-        double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
-        const int n16 = V.rows_bytes >> 4;
-        for (int g = tid; g < n16; g += WT_THREADS) {
-            const double2 l = pa[g], t = pb[g];
-            pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
-            pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));
+    const uint32_t bar = smem_u32(wt_sm);
+    // barriers: [0,NSTAGE) stage empty, [NSTAGE,2N) blob landed, [2N,3N) rows landed, [3N,4N) a1 done
+    auto b_empty = [&](int s) { return bar + 8u * s; };
+    auto b_blob = [&](int s) { return bar + 8u * (NSTAGE + s); };
+    auto b_rows = [&](int s) { return bar + 8u * (2 * NSTAGE + s); };
+    auto b_ready = [&](int s) { return bar + 8u * (3 * NSTAGE + s); };
+    int *next_item = reinterpret_cast<int *>(wt_sm + 8 * 4 * NSTAGE);
+    static_assert(8 * 4 * NSTAGE + 4 * NSTAGE <= WT_SMEM_HEAD, "smem head");
+    const int total = T.ntiles * ntracers;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(b_empty(s), NWC);
+            mbar_init(b_blob(s), 1);
+            mbar_init(b_rows(s), 1);
+            mbar_init(b_ready(s), 1);
         }
+        fence_mbar_init();
     }
     __syncthreads();
 
-    const double *g_lo = A.lo + tn;
-    const double *g_ai = A.area_inv;
-    const double *g_v = A.adf_v + blockIdx.y * A.ts_nodev;
-    for (int wi = warp; wi < V.n_witems; wi += WT_WARPS) {
-        bool act[NCH];
-        int z0[NCH], nz[NCH], cnt[NCH];
-        unsigned grow[NCH];
-        const int4 *en[NCH];
-        const unsigned char *ra[NCH], *rb[NCH], *re[NCH];
-        double hi[NCH][2], lw[NCH][2], p[NCH][2], m[NCH][2], l[NCH][2], ai[NCH][2];
-        int kmax = 0;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const unsigned d = V.sched[(wi * NCH + c) * 32 + lane];
-            act[c] = d != WT_IDLE;
-            const int4 hd = V.hdr[act[c] ? (d & 0xffu) : 0u];
-            z0[c] = act[c] ? (int)(d >> 8) * 2 : 0;
-            nz[c] = act[c] ? (hd.y & 0xff) : 0;
-            cnt[c] = act[c] ? (int)((unsigned)hd.w >> 16) : 0;
-            grow[c] = (unsigned)hd.x + (unsigned)z0[c];
-            en[c] = V.ent + (hd.w & 0xffff);
-            ra[c] = V.rowsA + z0[c] * 8;
-            rb[c] = V.rowsB + z0[c] * 8;
-            re[c] = V.erows + z0[c] * 8;
-            kmax = max(kmax, cnt[c]);
-            // ---- own column: global loads first, used after the gather ----
-            double f0 = 0., f1 = 0., f2 = 0.;
-            l[c][0] = l[c][1] = ai[c][0] = ai[c][1] = 0.;
-            if (act[c]) {
-                const double2 ll = __ldg(reinterpret_cast<const double2 *>(g_lo + grow[c]));
-                const double2 aa = __ldg(reinterpret_cast<const double2 *>(g_ai + grow[c]));
-                const double2 ff = __ldg(reinterpret_cast<const double2 *>(g_v + grow[c]));
-                if (z0[c] + 2 <= nz[c]) f2 = __ldg(g_v + grow[c] + 2);
-                l[c][0] = ll.x; l[c][1] = ll.y;
-                ai[c][0] = aa.x; ai[c][1] = aa.y;
-                f0 = ff.x; f1 = ff.y;
+    if (warp == 0) {
+        // ---- blob fetcher: refills a stage as soon as every consumer warp has left it ----
+        int it = 0;
+        for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+            const int s = it % NSTAGE;
+            mbar_wait(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+            if (lane == 0) {
+                const int tile = v % T.ntiles;
+                const unsigned b0 = __ldg(T.blob_off + tile), b1 = __ldg(T.blob_off + tile + 1);
+                next_item[s] = 0;
+                mbar_expect_tx(b_blob(s), (b1 - b0) * 16u);
+                bulk_g2s(smem_u32(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes), T.blob + b0, (b1 - b0) * 16u, b_blob(s));
             }
-            // cluster bounds start from the (-big, +big) fill of ring elements that already ended
-            // (reference.cpp:341-349) and the node's own a1 bounds
-            const int fm = (hd.y >> 8) & 0xff, sd = (hd.y >> 16) & 0xff;
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const bool fl = z0[c] + v >= fm;
-                hi[c][v] = fl ? -A.big : -CUDART_INF;
-                lw[c][v] = fl ? A.big : CUDART_INF;
-            }
-            {
-                const double2 x = *reinterpret_cast<const double2 *>(ra[c] + hd.z);
-                const double2 y = *reinterpret_cast<const double2 *>(rb[c] + hd.z);
-                if (act[c] && z0[c] < sd) {
-                    hi[c][0] = pick_max(hi[c][0], x.x);
-                    lw[c][0] = pick_min(lw[c][0], y.x);
-                }
-                if (act[c] && z0[c] + 1 < sd) {
-                    hi[c][1] = pick_max(hi[c][1], x.y);
-                    lw[c][1] = pick_min(lw[c][1], y.y);
-                }
-            }
-            wt_b1v(f0, f1, f2, p[c][0], p[c][1], m[c][0], m[c][1]);
+            __syncwarp();
         }
-        // ---- the node's edges in ascending edge id: a2/a3 bounds + b1 horizontal ----
-        for (int k = 0; k < kmax; ++k) {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                if (NCH == 1 || k < cnt[c]) {
-                    const int4 e = en[c][k];
-                    const double2 x = *reinterpret_cast<const double2 *>(ra[c] + e.y);
-                    const double2 y = *reinterpret_cast<const double2 *>(rb[c] + e.y);
-                    const double2 h = *reinterpret_cast<const double2 *>(re[c] + e.x);
-                    wt_edge_a(z0[c], e.z, x, y, h, hi[c][0], hi[c][1], lw[c][0], lw[c][1], p[c][0], p[c][1], m[c][0],
-                              m[c][1]);
+    } else if (warp <= NPW) {
+        // ---- copy issuers: one bulk copy per staged row, the list shared by NPW warps ----
+        int it = 0;
+        for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+            const int s = it % NSTAGE;
+            const int tr = v / T.ntiles;
+            mbar_wait(b_blob(s), (it / NSTAGE) & 1);
+            const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
+            // the transaction count may run negative until this arrives; the phase cannot complete before
+            if (warp == 1 && lane == 0) mbar_expect_tx(b_rows(s), (uint32_t)V.tx_bytes);
+            const double *ga = (PHASE_A ? A.lo : A.plus) + tr * A.ts_node;
+            const double *gb = (PHASE_A ? A.ttf : A.minus) + tr * A.ts_node;
+            const double *ge = A.adf_h_in + tr * A.ts_edge;
+            const uint32_t sa = smem_u32(V.rowsA);
+            for (int u = (warp - 1) * 32 + lane; u < V.n_copies; u += NPW * 32) {
+                const int2 r = V.copies[u];
+                const uint32_t so = ((uint32_t)r.y & 0xffffu) << 4, sz = (((uint32_t)r.y >> 16) & 0xffu) << 4;
+                const uint32_t arr = ((uint32_t)r.y >> 24) & 3u;
+                const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
+                bulk_g2s(sa + so, src, sz, b_rows(s));
+            }
+            __syncwarp();
+        }
+    } else if (PHASE_A && warp == NPW + 1) {
+        // ---- phase A: a1 in place on the landed rows, (fct_LO, ttf) -> (max, min), reference.cpp:315-316 ----
+        {
+            int it = 0;
+            for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+                const int s = it % NSTAGE;
+                mbar_wait(b_blob(s), (it / NSTAGE) & 1);
+                const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
+                mbar_wait(b_rows(s), (it / NSTAGE) & 1);
+                double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
+                const int n16 = V.rows_bytes >> 4;
+#pragma unroll 4
+                for (int g = lane; g < n16; g += 32) {
+                    const double2 l = pa[g], t = pb[g];
+                    pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
+                    pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));
                 }
+                fence_proxy_async();   // the next refill of this stage is written by the async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_ready(s));
             }
         }
-        // ---- vertical 3-point stencil of a3 (reference.cpp:380-392) through warp shuffles ----
-        double a0[NCH], a1[NCH], b0[NCH], b1[NCH], pmax[NCH], nmax[NCH], pmin[NCH], nmin[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            a0[c] = hi[c][0]; a1[c] = hi[c][1];
-            b0[c] = lw[c][0]; b1[c] = lw[c][1];
-        }
-        vl_neighbours<NCH>(a0, a1, lane, pmax, nmax);
-        vl_neighbours<NCH>(b0, b1, lane, pmin, nmin);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            if (!act[c]) continue;
-            double bm[2], bn[2];
-            {
-                double x = a0[c], y = b0[c];
-                if (z0[c] > 0 && z0[c] < nz[c] - 1) {
-                    x = pick_max(pick_max(pmax[c], x), a1[c]);
-                    y = pick_min(pick_min(pmin[c], y), b1[c]);
-                }
-                bm[0] = x - l[c][0];
-                bn[0] = y - l[c][0];
-                x = a1[c];
-                y = b1[c];
-                if (z0[c] + 1 < nz[c] - 1) {
-                    x = pick_max(pick_max(a0[c], x), nmax[c]);
-                    y = pick_min(pick_min(b0[c], y), nmin[c]);
-                }
-                bm[1] = x - l[c][1];
-                bn[1] = y - l[c][1];
+    } else {
+        // ---- consumers ----
+        auto grab = [&](int s) {
+            int wi = 0;
+            if (lane == 0) wi = atomicAdd(next_item + s, 1);
+            return __shfl_sync(0xffffffffu, wi, 0);
+        };
+        int it = 0;
+        for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+            const int s = it % NSTAGE;
+            const int tr = v / T.ntiles;
+            mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
+            const size_t tn = tr * A.ts_node;
+            const double *g_v = A.adf_v + tr * A.ts_nodev;
+            int wi = grab(s);
+            WtEarly E;
+            if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v);
+            while (wi < V.n_witems) {
+                const int wn = grab(s);
+                WtEarly En;
+                if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v);
+                if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, E);
+                else wt_item_b(A, V, wi, lane, tn, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E);
+                wi = wn;
+                E = En;
             }
-            // ---- b2, reference.cpp:432-435 ----
-            double pf[2], mf[2];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                double flux = p[c][v] * A.dt * ai[c][v] + A.eps;
-                pf[v] = pick_min(1., div_exact(bm[v], flux));
-                flux = m[c][v] * A.dt * ai[c][v] - A.eps;
-                mf[v] = pick_min(1., div_exact(bn[v], flux));
-            }
-            const size_t off = tn + grow[c];
-            if (z0[c] + 1 < nz[c]) {
-                *reinterpret_cast<double2 *>(A.ttf_max + off) = make_double2(bm[0], bm[1]);
-                *reinterpret_cast<double2 *>(A.ttf_min + off) = make_double2(bn[0], bn[1]);
-                *reinterpret_cast<double2 *>(A.plus + off) = make_double2(pf[0], pf[1]);
-                *reinterpret_cast<double2 *>(A.minus + off) = make_double2(mf[0], mf[1]);
-            } else {
-                A.ttf_max[off] = bm[0];
-                A.ttf_min[off] = bn[0];
-                A.plus[off] = pf[0];
-                A.minus[off] = mf[0];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Phase B = b3 vertical + b3 horizontal + c vertical + c horizontal
-// ------------------------------------------------------------------------------------------------
-template <int NCH, int MINB>
-__global__ void __launch_bounds__(WT_THREADS, MINB) k_phaseB_warp(Arrays A, WarpTilesDev T)
-{
-    extern __shared__ __align__(128) unsigned char wt_sm[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t tn = blockIdx.y * A.ts_node;
-    const WtView V = wt_stage(wt_sm, T, A.plus + tn, A.minus + tn, A.adf_h_in + blockIdx.y * A.ts_edge);
-    (void)lane;
-
-    const double *g_v = A.adf_v + blockIdx.y * A.ts_nodev;
-    double *g_vout = A.adf_v_out + blockIdx.y * A.ts_nodev;
-    double *g_ho = A.adf_h_out + blockIdx.y * A.ts_edge;
-    for (int wi = warp; wi < V.n_witems; wi += WT_WARPS) {
-        bool act[NCH];
-        int z0[NCH], nz[NCH], cnt[NCH];
-        unsigned grow[NCH];
-        const int4 *en[NCH];
-        const unsigned char *ra[NCH], *rb[NCH], *re[NCH];
-        double dh[NCH][2], dv[NCH][2], fl[NCH][2], ar[NCH][2], pn[NCH][2], mn[NCH][2];
-        int kmax = 0;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const unsigned d = V.sched[(wi * NCH + c) * 32 + lane];
-            act[c] = d != WT_IDLE;
-            const int4 hd = V.hdr[act[c] ? (d & 0xffu) : 0u];
-            z0[c] = act[c] ? (int)(d >> 8) * 2 : 0;
-            nz[c] = act[c] ? (hd.y & 0xff) : 0;
-            cnt[c] = act[c] ? (int)((unsigned)hd.w >> 16) : 0;
-            grow[c] = (unsigned)hd.x + (unsigned)z0[c];
-            en[c] = V.ent + (hd.w & 0xffff);
-            ra[c] = V.rowsA + z0[c] * 8;
-            rb[c] = V.rowsB + z0[c] * 8;
-            re[c] = V.erows + z0[c] * 8;
-            kmax = max(kmax, cnt[c]);
-            dh[c][0] = dh[c][1] = dv[c][0] = dv[c][1] = 0.;
-            fl[c][0] = fl[c][1] = ar[c][0] = ar[c][1] = 0.;
-            pn[c][0] = pn[c][1] = mn[c][0] = mn[c][1] = 0.;
-            if (act[c]) {
-                // ---- every global load of the own column ----
-                const size_t off = tn + grow[c];
-                const double2 q_dv = *reinterpret_cast<const double2 *>(A.del_v + off);
-                const double2 q_dh = *reinterpret_cast<const double2 *>(A.del_h + off);
-                const double2 q_t = __ldg(reinterpret_cast<const double2 *>(A.ttf + off));
-                const double2 q_l = __ldg(reinterpret_cast<const double2 *>(A.lo + off));
-                const double2 q_hn = __ldg(reinterpret_cast<const double2 *>(A.hnode + grow[c]));
-                const double2 q_hw = __ldg(reinterpret_cast<const double2 *>(A.hnode_new + grow[c]));
-                const double2 q_ar = __ldg(reinterpret_cast<const double2 *>(A.area + grow[c]));
-                const double2 q_f = __ldg(reinterpret_cast<const double2 *>(g_v + grow[c]));
-                const double f2 = (z0[c] + 2 <= nz[c]) ? __ldg(g_v + grow[c] + 2) : 0.;
-                // own factors from the staged rows: levels z0-1 .. z0+2
-                const unsigned char *pr = ra[c] + hd.z, *mr = rb[c] + hd.z;
-                const double2 pp = *reinterpret_cast<const double2 *>(pr);
-                const double2 mm = *reinterpret_cast<const double2 *>(mr);
-                const double p_m1 = *reinterpret_cast<const double *>(pr - 8);
-                const double m_m1 = *reinterpret_cast<const double *>(mr - 8);
-                const double p_p2 = *reinterpret_cast<const double *>(pr + 16);
-                const double m_p2 = *reinterpret_cast<const double *>(mr + 16);
-                pn[c][0] = pp.x; pn[c][1] = pp.y;
-                mn[c][0] = mm.x; mn[c][1] = mm.y;
-                // ---- b3 vertical, docs/refactoring.md:205-231 (the bottom flux stays) ----
-                const int z = z0[c];
-                double l0, l1, l2;
-                {
-                    double ae = 1.;
-                    if (z == 0) {
-                        ae = pick_min(ae, (q_f.x >= 0.) ? pp.x : mm.x);
-                    } else if (q_f.x >= 0.) {
-                        ae = pick_min(ae, m_m1);
-                        ae = pick_min(ae, pp.x);
-                    } else {
-                        ae = pick_min(ae, p_m1);
-                        ae = pick_min(ae, mm.x);
-                    }
-                    l0 = ae * q_f.x;
-                }
-                if (z + 1 < nz[c]) {
-                    double ae = 1.;
-                    if (q_f.y >= 0.) {
-                        ae = pick_min(ae, mm.x);
-                        ae = pick_min(ae, pp.y);
-                    } else {
-                        ae = pick_min(ae, pp.x);
-                        ae = pick_min(ae, mm.y);
-                    }
-                    l1 = ae * q_f.y;
-                } else {
-                    l1 = q_f.y;
-                }
-                if (z + 2 < nz[c]) {
-                    double ae = 1.;
-                    if (f2 >= 0.) {
-                        ae = pick_min(ae, mm.y);
-                        ae = pick_min(ae, p_p2);
-                    } else {
-                        ae = pick_min(ae, pp.y);
-                        ae = pick_min(ae, m_p2);
-                    }
-                    l2 = ae * f2;
-                } else {
-                    l2 = f2;
-                }
-                fl[c][0] = l0;
-                fl[c][1] = l1;
-                // ---- c vertical, docs/refactoring.md:295-300 ----
-                ar[c][0] = A.dt / q_ar.x;
-                ar[c][1] = A.dt / q_ar.y;
-                dv[c][0] = q_dv.x - q_t.x * q_hn.x + q_l.x * q_hw.x + (l0 - l1) * ar[c][0];
-                dv[c][1] = q_dv.y - q_t.y * q_hn.y + q_l.y * q_hw.y + (l1 - l2) * ar[c][1];
-                dh[c][0] = q_dh.x;
-                dh[c][1] = q_dh.y;
-            }
-        }
-        // ---- b3 horizontal + c horizontal over the node's edges, ascending edge id ----
-        for (int k = 0; k < kmax; ++k) {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                if (NCH == 1 || k < cnt[c]) {
-                    const int4 e = en[c][k];
-                    const double2 po = *reinterpret_cast<const double2 *>(ra[c] + e.y);
-                    const double2 mo = *reinterpret_cast<const double2 *>(rb[c] + e.y);
-                    const double2 h = *reinterpret_cast<const double2 *>(re[c] + e.x);
-                    double hl0, hl1;
-                    wt_edge_b(z0[c], e.z, po, mo, h, pn[c][0], pn[c][1], mn[c][0], mn[c][1], ar[c][0], ar[c][1],
-                              dh[c][0], dh[c][1], hl0, hl1);
-                    const int dg = e.z & 0xffff;
-                    if ((e.z & 0x40000000) && z0[c] < dg) {
-                        double *o = g_ho + (unsigned)e.w + z0[c];
-                        if (z0[c] + 1 < dg) *reinterpret_cast<double2 *>(o) = make_double2(hl0, hl1);
-                        else o[0] = hl0;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            if (!act[c]) continue;
-            const size_t off = tn + grow[c];
-            if (z0[c] + 1 < nz[c]) {
-                *reinterpret_cast<double2 *>(g_vout + grow[c]) = make_double2(fl[c][0], fl[c][1]);
-                *reinterpret_cast<double2 *>(A.del_v + off) = make_double2(dv[c][0], dv[c][1]);
-                *reinterpret_cast<double2 *>(A.del_h + off) = make_double2(dh[c][0], dh[c][1]);
-            } else {
-                g_vout[grow[c]] = fl[c][0];
-                A.del_v[off] = dv[c][0];
-                A.del_h[off] = dh[c][0];
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_empty(s));
         }
     }
 }

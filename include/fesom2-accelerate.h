@@ -195,7 +195,7 @@ void fct_ale_plan_destroy_(void **plan, int *istat);
 void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D, int *myDim_edge2D,
                            int *nl, int *nlevels_nod2D, int *nlevels_elem2D, int *elem2D_nodes,
                            int *nod_in_elem2D_num, int *nod_in_elem2D, int *nod_in_elem2D_dim,
-                           int *edges, int *edge_tri, int *tile_nodes, int *nch, int *smem_cap,
+                           int *edges, int *edge_tri, int *tile_nodes, int *smem_cap,
                            int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
                            unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat);
 /* pitch (in doubles) of every padded device row of this plan: nl rounded up to an even count */

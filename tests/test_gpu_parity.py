@@ -26,7 +26,7 @@ def check(got, want, keys=OUT_KEYS, exact=True, owned=None):
 
 
 def cases(mesh_mod, name):
-    if name == "deep":        # DART-depth columns: two virtual-lane chunks per lane in the warp-item kernels
+    if name == "deep":        # DART-depth columns: 40 level pairs, cut across warp items with ghost slots
         m = mesh_mod.make_mesh(48, 37, 80, seed=3)
         return m, mesh_mod.make_fields(m, seed=4)
     if name == "adversarial":
@@ -81,15 +81,16 @@ def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
 
 
 @pytest.mark.parametrize("name", ["pi", "deep"])
-@pytest.mark.parametrize("knobs", [dict(WT_NCH=2), dict(WT_NODES=5), dict(WT_NODES=200, WT_SMEM=200 * 1024),
-                                   dict(WT_MINB_A=1, WT_MINB_B=1)])
+@pytest.mark.parametrize("knobs", [dict(WT_STAGES=2), dict(WT_NODES=5), dict(WT_NODES=200, WT_SMEM=110 * 1024),
+                                   dict(WT_WARPS_A=10, WT_WARPS_B=11, WT_ISSUERS=2),
+                                   dict(WT_WARPS_A=16, WT_WARPS_B=13, WT_ISSUERS=6, WT_SMEM=20 * 1024)])
 def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, knobs):
-    """The warp-item kernels must not depend on their tiling: chunk count, tile size (tiny tiles:
-    almost every neighbour row is a halo row; one huge tile per CTA), register bound."""
+    """The warp-item kernels must not depend on their tiling: ring depth, tile size (tiny tiles:
+    almost every neighbour row is a halo row; huge tiles: two stages only), consumer warps."""
     m, f = cases(mesh_mod, name)
     want = f.copy()
     oracle_mod.fct_ale(m, want)
-    defaults = dict(WT_NCH=0, WT_NODES=0, WT_SMEM=0, WT_MINB_A=0, WT_MINB_B=0)
+    defaults = dict(WT_STAGES=3, WT_NODES=0, WT_SMEM=0, WT_WARPS_A=0, WT_WARPS_B=0, WT_ISSUERS=0)
     try:
         for k, v in knobs.items():
             abi.tune(k, v)

@@ -15,7 +15,7 @@ from conftest import bits_equal
 INF = float("inf")
 
 
-def inspect(abi, m, tile_nodes=64, nch=1, smem_cap=74 * 1024, which=0):
+def inspect(abi, m, tile_nodes=64, smem_cap=74 * 1024, which=0):
     lib = abi.load()
     cap_words = 64 * 1024 * 1024 // 4
     blob = np.zeros(cap_words, np.uint32)
@@ -27,7 +27,7 @@ def inspect(abi, m, tile_nodes=64, nch=1, smem_cap=74 * 1024, which=0):
         abi.ci(m.nl), abi.iptr(m.nlevels_nod2D), abi.iptr(m.nlevels_elem),
         abi.iptr(m.elem2D_nodes.reshape(-1)), abi.iptr(m.nod_in_elem2D_num),
         abi.iptr(m.nod_in_elem2D.reshape(-1)), abi.ci(m.nod_in_elem2D_dim), abi.iptr(m.edges.reshape(-1)),
-        abi.iptr(m.edge_tri.reshape(-1)), abi.ci(tile_nodes), abi.ci(nch), abi.ci(smem_cap), abi.ci(which),
+        abi.iptr(m.edge_tri.reshape(-1)), abi.ci(tile_nodes), abi.ci(smem_cap), abi.ci(which),
         C.byref(C.c_longlong(cap_words * 4)), blob.ctypes.data_as(u32p), abi.ci(off.size),
         off.ctypes.data_as(u32p), C.byref(nt), C.byref(sm), C.byref(st))
     return st.value, nt.value, sm.value, blob, off
@@ -36,39 +36,36 @@ def inspect(abi, m, tile_nodes=64, nch=1, smem_cap=74 * 1024, which=0):
 class Tile:
     """Decoded blob of one tile + the shared-memory image the kernels build from it."""
 
-    def __init__(self, words, P, nch):
+    def __init__(self, words, P):
         b = words.tobytes()
         h = np.frombuffer(b, np.int32, 16)
-        (self.n_rows, self.n_erows, self.n_nodes, self.n_witems, off_erows, off_hdr, off_ent, off_sched,
+        (self.n_copies, self.n_erows, self.n_nodes, self.n_witems, self.n_rows, off_hdr, off_ent, off_sched,
          blob_bytes, self.rows_bytes, self.erows_bytes, self.tx) = [int(x) for x in h[:12]]
         assert blob_bytes == len(b)
-        self.rows = np.frombuffer(b, np.uint32, 2 * self.n_rows, 64).reshape(-1, 2)
-        self.erows = np.frombuffer(b, np.uint32, 2 * self.n_erows, off_erows).reshape(-1, 2)
+        self.copies = np.frombuffer(b, np.uint32, 2 * self.n_copies, 64).reshape(-1, 2)
         self.hdr = np.frombuffer(b, np.uint32, 4 * self.n_nodes, off_hdr).reshape(-1, 4)
         n_ent = (off_sched - off_ent) // 16
         self.ent = np.frombuffer(b, np.uint32, 4 * n_ent, off_ent).reshape(-1, 4)
-        self.sched = np.frombuffer(b, np.uint16, self.n_witems * 32 * nch, off_sched).reshape(self.n_witems, 32 * nch)
+        self.sched = np.frombuffer(b, np.uint16, self.n_witems * 32, off_sched).reshape(self.n_witems, 32)
         self.P = P
 
     def stage(self, src_a, src_b, src_e):
-        """the bulk copies of wt_stage: returns (rowsA, rowsB, erows) as float64 images (NaN = never written)"""
-        A = np.full(self.rows_bytes // 8 + 2 * self.P, np.nan)
-        B = A.copy()
-        Ee = np.full(self.erows_bytes // 8 + 2 * self.P, np.nan)
+        """the bulk copies of the issuer warps: returns (rowsA, rowsB, erows) as float64 images (NaN = never
+        written); the three regions are consecutive in the stage"""
+        ra, re = self.rows_bytes // 8, self.erows_bytes // 8
+        img = np.full(2 * ra + re + 2 * self.P, np.nan)
+        src = (src_a, src_b, src_e)
+        lim = (ra, 2 * ra, 2 * ra + re)
         tx = 0
-        for goff, pk in self.rows:
-            so, sz = (int(pk) & 0xffff) * 2, (int(pk) >> 16) * 2       # in doubles
-            assert so + sz <= self.rows_bytes // 8
-            A[so:so + sz] = src_a[goff:goff + sz]
-            B[so:so + sz] = src_b[goff:goff + sz]
-            tx += 2 * sz * 8
-        for goff, pk in self.erows:
-            so, sz = (int(pk) & 0xffff) * 2, (int(pk) >> 16) * 2
-            assert so + sz <= self.erows_bytes // 8
-            Ee[so:so + sz] = src_e[goff:goff + sz]
+        for goff, pk in self.copies:
+            pk = int(pk)
+            so, sz, arr = (pk & 0xffff) * 2, ((pk >> 16) & 0xff) * 2, (pk >> 24) & 3     # in doubles
+            assert sz > 0 and arr < 3 and so + sz <= lim[arr] and so >= (0, ra, 2 * ra)[arr]
+            assert np.isnan(img[so:so + sz]).all(), "two copies overlap"
+            img[so:so + sz] = src[arr][goff:goff + sz]
             tx += sz * 8
         assert tx == self.tx
-        return A, B, Ee
+        return img[:ra + 2 * self.P].copy(), img[ra:2 * ra + 2 * self.P].copy(), img[2 * ra:].copy()
 
 
 def pmax(a, b):
@@ -85,7 +82,7 @@ def pad(a, P):
     return out.reshape(-1)
 
 
-def emulate(m, f, blob, off, ntiles, nch):
+def emulate(m, f, blob, off, ntiles):
     """Both fused phases on the padded layout; returns the dict of padded result arrays."""
     P = (m.nl + 1) & ~1
     L = m.L
@@ -95,11 +92,11 @@ def emulate(m, f, blob, off, ntiles, nch):
     g["adf_v_out"] = g["fct_adf_v"].copy()
     g["adf_h_out"] = g["fct_adf_h"].copy()
     dt, eps, big = f.dt, f.flux_eps, f.bignumber
-    W = 32 * nch
+    W = 32
     seen_slots = set()
     for phase in "AB":
         for t in range(ntiles):
-            T = Tile(blob[off[t] * 4: off[t + 1] * 4], P, nch)
+            T = Tile(blob[off[t] * 4: off[t + 1] * 4], P)
             if phase == "A":
                 RA, RB, RE = T.stage(g["fct_LO"], g["ttf"], g["fct_adf_h"])
                 lo_, tt_ = RA.copy(), RB.copy()
@@ -115,16 +112,16 @@ def emulate(m, f, blob, off, ntiles, nch):
                     if d == 0xffff:
                         lanes.append(None)
                         continue
-                    ln, z0 = d & 0xff, (d >> 8) * 2
+                    ln, z0, ghost = d & 0xff, ((d >> 8) & 0x7f) * 2, bool(d >> 15)
                     hx, hy, hz, hw = [int(x) for x in T.hdr[ln]]
-                    lanes.append(dict(ln=ln, z0=z0, grow=hx + z0, nz=hy & 0xff, fm=(hy >> 8) & 0xff, sd=(hy >> 16) & 0xff,
-                                      own=hz // 8, e0=hw & 0xffff, cnt=hw >> 16))
-                    if phase == "A":
-                        assert (t, ln, z0) not in seen_slots
+                    lanes.append(dict(ln=ln, z0=z0, ghost=ghost, grow=hx + z0, nz=hy & 0xff, fm=(hy >> 8) & 0xff,
+                                      sd=(hy >> 16) & 0xff, own=hz // 8, e0=hw & 0xffff, cnt=hw >> 16))
+                    if phase == "A" and not ghost:
+                        assert (t, ln, z0) not in seen_slots        # every slot is computed exactly once
                         seen_slots.add((t, ln, z0))
-                # slots of a node are consecutive virtual lanes and complete
+                # the stencil neighbours of every real slot are the neighbouring lanes (ghosts included)
                 for vl, s in enumerate(lanes):
-                    if s is None:
+                    if s is None or s["ghost"]:
                         continue
                     assert s["z0"] < s["nz"]
                     if s["z0"] > 0:
@@ -137,6 +134,11 @@ def emulate(m, f, blob, off, ntiles, nch):
                     phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big)
                 else:
                     phase_b_item(T, lanes, RA, RB, RE, g, dt)
+            if phase == "A":
+                # all active slots of the tile's nodes are scheduled
+                for ln in range(T.n_nodes):
+                    nz = int(T.hdr[ln][1]) & 0xff
+                    assert all((t, ln, z) in seen_slots for z in range(0, nz, 2))
     return g, P
 
 
@@ -173,7 +175,7 @@ def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
         s.update(hi=hi, lw=lw, p=p, m=mm)
         tv.append(s)
     for vl, s in enumerate(tv):
-        if s is None:
+        if s is None or s["ghost"]:
             continue
         z0, nz = s["z0"], s["nz"]
         for v in range(2):
@@ -201,7 +203,7 @@ def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
 
 def phase_b_item(T, lanes, RA, RB, RE, g, dt):
     for s in lanes:
-        if s is None:
+        if s is None or s["ghost"]:
             continue
         z0, nz, own = s["z0"], s["nz"], s["own"]
         fv = g["fct_adf_v"]
@@ -270,24 +272,36 @@ def compare(m, f, g, P, want, owned=None):
         assert bits_equal(unpad(g["adf_h_out"], P, L), want.fct_adf_h)
 
 
-@pytest.mark.parametrize("name,nch,tn,cap", [("tiny", 1, 64, 74 * 1024), ("tiny", 2, 3, 74 * 1024),
-                                             ("pi", 1, 64, 74 * 1024), ("pi", 2, 24, 24 * 1024)])
-def test_tables_reproduce_the_oracle(mesh_mod, abi, oracle_mod, name, nch, tn, cap):
+@pytest.mark.parametrize("name,tn,cap", [("tiny", 64, 74 * 1024), ("tiny", 3, 74 * 1024),
+                                         ("pi", 96, 74 * 1024), ("pi", 24, 24 * 1024)])
+def test_tables_reproduce_the_oracle(mesh_mod, abi, oracle_mod, name, tn, cap):
     m = mesh_mod.make_workload(name)
     f = mesh_mod.make_fields(m)
     want = f.copy()
     oracle_mod.fct_ale(m, want)
-    st, nt, smem, blob, off = inspect(abi, m, tn, nch, cap)
+    st, nt, smem, blob, off = inspect(abi, m, tn, cap)
     assert st == 0 and nt >= 1 and smem <= cap
-    g, P = emulate(m, f, blob, off, nt, nch)
+    g, P = emulate(m, f, blob, off, nt)
     compare(m, f, g, P, want)
 
 
-def test_deep_columns_need_two_chunks(mesh_mod, abi):
+def test_deep_columns_are_cut_with_ghost_slots(mesh_mod, abi, oracle_mod):
+    """nl = 80: a full column has 40 level pairs, more than a 32-lane item -> cut, ghosts on both sides."""
     m = mesh_mod.make_mesh(12, 9, 80, seed=3)
-    assert inspect(abi, m, 64, 1, 112 * 1024)[0] == 2        # 40 level pairs do not fit 32 lanes
-    st, nt, smem, blob, off = inspect(abi, m, 64, 2, 112 * 1024)
-    assert st == 0 and smem <= 112 * 1024
+    f = mesh_mod.make_fields(m, seed=4)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    st, nt, smem, blob, off = inspect(abi, m, 64, 74 * 1024)
+    assert st == 0 and smem <= 74 * 1024
+    ghosts = 0
+    P = (m.nl + 1) & ~1
+    for t in range(nt):
+        T = Tile(blob[off[t] * 4: off[t + 1] * 4], P)
+        live = T.sched[T.sched != 0xffff]
+        ghosts += int((live >> 15).sum())
+    assert ghosts > 0
+    g, P = emulate(m, f, blob, off, nt)
+    compare(m, f, g, P, want)
 
 
 def test_non_triangulation_is_refused(mesh_mod, abi):
@@ -310,11 +324,11 @@ def test_partitioned_tables(mesh_mod, abi, oracle_mod):
     gminus = np.array(f.fct_minus)
     runs = []
     for p, lf in zip(parts, lfs):
-        tabs = [inspect(abi, p.mesh, 16, 1, 74 * 1024, which) for which in (1, 2)]
+        tabs = [inspect(abi, p.mesh, 16, 74 * 1024, which) for which in (1, 2)]
         assert all(t[0] == 0 for t in tabs)
         runs.append(tabs)
         for st, nt, smem, blob, off in tabs:
-            g, P = emulate(p.mesh, lf, blob, off, nt, 1)
+            g, P = emulate(p.mesh, lf, blob, off, nt)
             n = p.mesh.myDim_nod2D
             own = np.zeros(p.mesh.nnod, bool)
             # rows this tile set wrote = nodes whose fct_plus changed from the input
