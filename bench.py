@@ -9,10 +9,13 @@ A "step" is one fct_ale pass a1..c over one tracer of the workload mesh.  Produc
   value     device-resident fused step (fct_ale_step_, mode 1), inputs already in HBM, timed with
             CUDA events on the launching stream, max over ranks.  N>1: the SAME mesh split into N
             partitions (strong scaling), halo of fct_plus/fct_minus over NVLink inside the step.
-  e2e       the reference-facing handle ABI exactly as FESOM2's Fortran drives the reference
-            library (transfer_var_async_ -> fct_ale_pre_comm_acc_ -> await -> inter -> post ->
-            fct_ale_c_acc_) on page-locked HOST arrays; every H2D / D2H copy is inside the timed
-            region (N>1: plus the host exchange_nod between pre_comm and post_comm, over gloo).
+  e2e       the same step for a caller whose fields live on the HOST, through the C ABI
+            (fct_ale_field_upload_ x8 -> fct_ale_step_ -> fct_ale_field_download_ x2 ->
+            await_stream_) on page-locked arrays: every step uploads its inputs (ttf, fct_LO,
+            fct_adf_v, fct_adf_h, hnode, hnode_new, del_ttf_adv*) and downloads the tendencies, all
+            inside the timed region.  `e2e.reference_sequence` is the reference library's own call
+            sequence (transfer_var_async_ -> fct_ale_pre_comm_acc_ -> await -> inter -> post ->
+            fct_ale_c_acc_, five PCIe crossings per step; N>1: plus the host exchange_nod over gloo).
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event launch time vs the measured
             HBM peak (MEASURED_PEAKS.json).
   cpu_baseline  the reference's CPU code timed on this box (rank 0, N=1), bounded sample.
@@ -233,13 +236,13 @@ def run_product(args):
     algA = 8 * (8 * Sn + Sg) + 16 * m.myDim_nod2D
     algB = 8 * (13 * Sn + 2 * Sg)
     kern = {}
+    suffix = {"warp": "_warp", "tile": "_tile", "untiled": ""}[plan.kernels]
+    mode_name = {"warp": "persistent TMA-staged warp-item fused phases A+B", "tile": "tile-staged fused phases A+B",
+                 "untiled": "untiled fused phases A+B"}[plan.kernels]
     if world == 1:
-        for name, alg in (("phaseA_tile", algA), ("phaseB_tile", algB)):
-            try:
-                df.stage(name, f, sync=True)
-            except abi.AbiError:
-                name = name.replace("_tile", "")
-                df.stage(name, f, sync=True)
+        for base, alg in (("phaseA", algA), ("phaseB", algB)):
+            name = base + suffix                  # the kernels fct_ale_step_ mode 1 runs on this plan
+            df.stage(name, f, sync=True)
             reps = max(3, min(args.steps, 10))
             e0.record(df.stream)
             for _ in range(reps):
@@ -254,7 +257,7 @@ def run_product(args):
                 traffic = json.load(fh).get(args.workload, {}).get(dom)
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": dalg / dms / 1e6, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": {"phaseA_warp": "k_phase_warp<true,...>", "phaseB_warp": "k_phase_warp<false,...>"}.get(dom, "k_" + dom), "achieved": dalg / dms / 1e6, "peak": peak, "unit": "GB/s",
                     "frac": dalg / dms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": dalg, "ms_per_launch": dms,
                     "kernels": {k: {"ms": v[0], "alg_GBs": v[1] / v[0] / 1e6, "frac": v[1] / v[0] / 1e6 / peak} for k, v in kern.items()}}
@@ -262,30 +265,45 @@ def run_product(args):
         roofline = {"bound": "hbm", "kernel": "fct_ale_step (both fused phases + halo)", "achieved": bytes_alg_total / world / ms_step / 1e6,
                     "peak": peak, "unit": "GB/s", "frac": bytes_alg_total / world / ms_step / 1e6 / peak, "traffic": None,
                     "peak_source": peak_src, "note": "per-GPU average over the whole step"}
+    log(f"value done: {ms_step:.3f} ms/step ({time.time() - t_setup:.1f}s)")
+
+    # ---------------- e2e: host-resident caller, device-resident step ----------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    assert df.host_step(f, f, mode=1, halo=halo) == 10       # warm-up
+    hostcomm.barrier()
+    ta = time.perf_counter()
+    for _ in range(e2e_steps):
+        df.host_step(f, f, mode=1, halo=halo)  # ends with await_stream_: the tendencies are on the host
+    tb = time.perf_counter()
+    e2e_s = hostcomm.max_over_ranks((tb - ta) / e2e_steps)
+    hb, db = df.host_step_bytes(f)
+    h2d, d2h = hostcomm.sum_over_ranks(hb), hostcomm.sum_over_ranks(db)
     if halo is not None:
         halo.free()
     df.free()
     plan.free()
-    log(f"value done: {ms_step:.3f} ms/step ({time.time() - t_setup:.1f}s)")
-
-    # ---------------- e2e: the reference's call sequence on host arrays ----------------
-    exchange = None
-    if world > 1:
-        def exchange(ff):
-            hostcomm.exchange_nod(part, [ff.fct_plus, ff.fct_minus])
-    ch = harness.HandleChain(m, f, with_c=True)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    ch.step(exchange)                          # warm-up (also builds the cached plan)
-    hostcomm.barrier()
-    ta = time.perf_counter()
-    for _ in range(e2e_steps):
-        ch.step(exchange)                      # ends with await_stream_: results are on the host
-    tb = time.perf_counter()
-    e2e_s = hostcomm.max_over_ranks((tb - ta) / e2e_steps)
-    h2d = hostcomm.sum_over_ranks(ch.h2d_bytes())
-    d2h = hostcomm.sum_over_ranks(ch.d2h_bytes())
-    ch.free()
     log(f"e2e done: {e2e_s * 1e3:.1f} ms/step ({time.time() - t_setup:.1f}s)")
+
+    # ---------------- the reference library's own call sequence on host arrays (context) ----------------
+    refseq = None
+    if not args.no_refseq:
+        exchange = None
+        if world > 1:
+            def exchange(ff):
+                hostcomm.exchange_nod(part, [ff.fct_plus, ff.fct_minus])
+        ch = harness.HandleChain(m, f, with_c=True)
+        ch.step(exchange)                          # warm-up (also builds the cached plan)
+        hostcomm.barrier()
+        ta = time.perf_counter()
+        ch.step(exchange)                          # ends with await_stream_: results are on the host
+        tb = time.perf_counter()
+        rs = hostcomm.max_over_ranks(tb - ta)
+        refseq = {"value": Sn_total / rs, "unit": UNIT, "ms_per_step": rs * 1e3, "steps": 1,
+                  "h2d_bytes_per_step": int(hostcomm.sum_over_ranks(ch.h2d_bytes())),
+                  "d2h_bytes_per_step": int(hostcomm.sum_over_ranks(ch.d2h_bytes())),
+                  "api": "transfer_var_async_ / fct_ale_pre_comm_acc_ / inter / post / fct_ale_c_acc_ (reference call sequence, stage kernels)"}
+        ch.free()
+        log(f"reference call sequence done: {rs * 1e3:.1f} ms/step ({time.time() - t_setup:.1f}s)")
 
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu = None
@@ -304,14 +322,15 @@ def run_product(args):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "nodes": N_total, "levels": w["nl"], "tracers": 1, "partitions": world,
-                           "node_level_updates": Sn_total, "mode": "fused tile-staged phases A+B", "device": devname,
+                           "node_level_updates": Sn_total, "mode": mode_name, "device": devname,
                            "l2": "inputs (tens of GB) far larger than the 126 MB L2; no flush needed",
                            "alg_bytes_per_step": bytes_alg_total},
                 "hbm": {"alg_GBs_per_gpu": bytes_alg_total / world / ms_step / 1e6, "frac_of_peak": bytes_alg_total / world / ms_step / 1e6 / peak},
                 "clocks": clocks,
                 "e2e": {"value": Sn_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                        "api": "transfer_var_async_ / fct_ale_pre_comm_acc_ / inter / post / fct_ale_c_acc_ (reference call sequence)"},
+                        "api": "fct_ale_field_upload_ x8 / fct_ale_step_ / fct_ale_field_download_ x2 / await_stream_ on page-locked host arrays",
+                        "reference_sequence": refseq},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "setup_s": time.time() - t_setup}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -329,6 +348,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("FCT_BENCH_WORKLOAD", "ng5"))
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-refseq", action="store_true", help="skip the timing of the reference library's call sequence")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -25,7 +25,7 @@ SYMBOLS = [
     "free_pinned_doubles_", "free_stream_", "fct_ale_set_fused_", "fct_ale_tune_", "fct_ale_launch_count_",
     "fct_ale_device_info_", "fct_ale_event_create_", "fct_ale_event_record_",
     "fct_ale_event_elapsed_ms_", "fct_ale_event_destroy_", "fct_ale_mem_info_",
-    "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_", "fct_ale_plan_inspect_",
+    "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_", "fct_ale_plan_inspect_", "fct_ale_plan_kernels_",
     "fct_ale_fields_create_", "fct_ale_fields_destroy_", "fct_ale_field_upload_",
     "fct_ale_field_download_", "fct_ale_step_", "fct_ale_stage_",
     "fct_ale_comm_unique_id_", "fct_ale_halo_create_", "fct_ale_halo_destroy_",

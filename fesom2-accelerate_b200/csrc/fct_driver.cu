@@ -308,7 +308,7 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
     p->wtiles_ok = true;
 }
 
-typedef void (*warp_kern_t)(Arrays, WarpTilesDev, int, int);
+typedef void (*warp_kern_t)(Arrays, WarpTilesDev, int, int, int *);
 struct WarpVariant {
     warp_kern_t fn;
     bool phase_a;
@@ -344,7 +344,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     }
     // consumer / issuer warps: the closest compiled variant (0: default)
     int nwc = env_int(isA ? "FCT_WT_WARPS_A" : "FCT_WT_WARPS_B", 0), npw = env_int("FCT_WT_ISSUERS", 0);
-    nwc = nwc <= 0 ? (isA ? 18 : 15) : nwc;
+    nwc = nwc <= 0 ? (isA ? 18 : 11) : nwc;   // phase B needs ~110 registers: 16 warps in all
     npw = npw <= 0 ? 4 : npw;
     constexpr int NV = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     int vi = -1, best = 1 << 30;
@@ -376,8 +376,29 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         sms = std::max(sms, 1);
     }
     const long long total = (long long)T.ntiles * ntracers;
+    if (total >= (1LL << 30)) {
+        std::fprintf(stderr, "fesom2-accelerate: too many (tile, tracer) pairs for one launch\n");
+        return false;
+    }
+    // device-wide tile counters: a ring of self-rearming pairs, one per launch in flight
+    static int *ctr_ring = nullptr;
+    static std::atomic<unsigned> ctr_next{0};
+    constexpr unsigned CTR_SLOTS = 256;
+    int *ctr = nullptr;
+    if (env_int("FCT_WT_DYNAMIC", 1)) {
+        static std::mutex ring_mutex;
+        std::lock_guard<std::mutex> lock(ring_mutex);
+        if (!ctr_ring) {
+            if (!cuda_ok(cudaMalloc(&ctr_ring, CTR_SLOTS * 2 * sizeof(int)), "cudaMalloc(counters)") ||
+                !cuda_ok(cudaMemset(ctr_ring, 0, CTR_SLOTS * 2 * sizeof(int)), "cudaMemset(counters)")) {
+                ctr_ring = nullptr;
+                return false;
+            }
+        }
+        ctr = ctr_ring + 2 * (ctr_next.fetch_add(1) % CTR_SLOTS);
+    }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
-    v.fn<<<grid, (v.issuers + 1 + (isA ? 1 : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes);
+    v.fn<<<grid, (v.issuers + 1 + (isA ? 1 : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");
 }
@@ -455,7 +476,7 @@ Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, co
     Plan *p = new (std::nothrow) Plan;
     if (!p) return nullptr;
     p->N = N; p->H = H; p->E = E; p->G = G; p->nl = nl; p->nie_dim = nie_dim;
-    p->pitch = (nl + 1) & ~1;
+    p->pitch = (nl + 7) & ~7;   // rows start on 64-byte boundaries: no DRAM sector is shared by two rows
     p->owns_mesh = true;
     auto up = [&](const int *src, size_t n) -> const int * {
         std::vector<int> v(src, src + n);

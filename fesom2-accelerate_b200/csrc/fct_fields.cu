@@ -4,6 +4,7 @@
 // optionally split into boundary / interior node sets around the NVLink halo exchange.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -87,6 +88,18 @@ static Arrays arrays_of(const Fields *f, int mode, double dt, double eps, double
     return A;
 }
 
+// dense host rows (width W) <-> padded device rows (pitch P).  A strided cudaMemcpy2D of 400..600-byte
+// rows runs at a few GB/s over PCIe; one contiguous copy plus this repack runs at link speed.
+__global__ void k_repack(double *__restrict__ dst, const double *__restrict__ src, size_t rows, int W, int dpitch, int spitch)
+{
+    const size_t n = rows * (size_t)W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (size_t)W;
+        const int c = (int)(i - r * (size_t)W);
+        dst[r * (size_t)dpitch + c] = src[r * (size_t)spitch + c];
+    }
+}
+
 static bool run_stage(Fields *f, const Arrays &A, int stage, const int *list, int first, int count, cudaStream_t s)
 {
     return launch_stage(stage, 2, A, f->plan->dev, list, first, count, f->T, s);
@@ -125,6 +138,13 @@ void fct_ale_plan_destroy_(void **plan, int *istat)
     *istat = p ? 0 : 1;
     if (p) destroy_plan(p);
     if (plan) *plan = nullptr;
+}
+
+void fct_ale_plan_kernels_(void **plan, int *warp_tiles, int *staged_tiles)
+{
+    Plan *p = P_(plan);
+    *warp_tiles = (p && p->wtiles_ok) ? 1 : 0;
+    *staged_tiles = (p && p->tiles_ok) ? 1 : 0;
 }
 
 void fct_ale_plan_pitch_(void **plan, int *pitch)
@@ -174,6 +194,7 @@ void fct_ale_fields_destroy_(void **fields, int *istat)
     if (!f) return;
     for (double *b : f->buf)
         if (b) cudaFree(b);
+    if (f->stage) cudaFree(f->stage);
     f->magic = 0;
     delete f;
     *fields = nullptr;
@@ -196,9 +217,51 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
         *istat = 0;
         return;
     }
-    cudaError_t e = up ? cudaMemcpy2DAsync(d, pitch, host, width, width, rows, cudaMemcpyHostToDevice, S_(stream))
-                       : cudaMemcpy2DAsync(host, width, d, pitch, width, rows, cudaMemcpyDeviceToHost, S_(stream));
-    *istat = cuda_ok(e, up ? "field upload" : "field download") ? 0 : 1;
+    cudaStream_t st = S_(stream);
+    if (width == pitch) {
+        cudaError_t e = up ? cudaMemcpyAsync(d, host, rows * pitch, cudaMemcpyHostToDevice, st)
+                           : cudaMemcpyAsync(host, d, rows * pitch, cudaMemcpyDeviceToHost, st);
+        *istat = cuda_ok(e, up ? "field upload" : "field download") ? 0 : 1;
+        return;
+    }
+    // one contiguous PCIe copy through a dense staging buffer + a repack kernel (stream ordered, so
+    // the single buffer serves any sequence of transfers on one stream; callers that spread
+    // transfers of one Fields object over several streams must order them themselves)
+    const size_t W = width / sizeof(double), Pd = pitch / sizeof(double), need = rows * W;
+    if (need > f->stage_doubles) {
+        cudaStreamSynchronize(st);
+        if (f->stage) cudaFree(f->stage);
+        f->stage = nullptr;
+        f->stage_doubles = 0;
+        size_t want = need;   // size it once for the largest field of this object
+        for (int id = 0; id < FCT_FIELD_COUNT; ++id) {
+            if (!f->buf[id]) continue;
+            const FieldMeta mm = meta_of(id);
+            want = std::max(want, field_rows(f, mm.kind) * (size_t)(f->plan->nl - mm.width_minus) * (id == FCT_UV_RHS ? 2 : 1));
+        }
+        if (!cuda_ok(cudaMalloc(&f->stage, want * sizeof(double)), "cudaMalloc(staging)")) {
+            if (!cuda_ok(cudaMalloc(&f->stage, need * sizeof(double)), "cudaMalloc(staging)")) return;
+            want = need;
+        }
+        f->stage_doubles = want;
+    }
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((need + threads - 1) / threads, (size_t)148 * 16);
+    bool ok;
+    if (up) {
+        ok = cuda_ok(cudaMemcpyAsync(f->stage, host, need * sizeof(double), cudaMemcpyHostToDevice, st), "field upload");
+        if (ok) {
+            k_repack<<<blocks, threads, 0, st>>>(d, f->stage, rows, (int)W, (int)Pd, (int)W);
+            count_launch(1);
+            ok = cuda_ok(cudaGetLastError(), "repack");
+        }
+    } else {
+        k_repack<<<blocks, threads, 0, st>>>(f->stage, d, rows, (int)W, (int)W, (int)Pd);
+        count_launch(1);
+        ok = cuda_ok(cudaGetLastError(), "repack") &&
+             cuda_ok(cudaMemcpyAsync(host, f->stage, need * sizeof(double), cudaMemcpyDeviceToHost, st), "field download");
+    }
+    *istat = ok ? 0 : 1;
 }
 
 void fct_ale_field_upload_(void **fields, int *field, int *tracer, real_type *host, void **stream, int *istat)

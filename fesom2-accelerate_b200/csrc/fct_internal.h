@@ -40,6 +40,8 @@ struct Fields {
     size_t rows = 0;   // N + H
     double *buf[FCT_FIELD_COUNT_INTERNAL] = {nullptr};
     size_t ts_node = 0, ts_edge = 0, ts_uv = 0;
+    double *stage = nullptr;   // dense staging buffer of field_upload_ / field_download_
+    size_t stage_doubles = 0;
 };
 
 struct Halo;

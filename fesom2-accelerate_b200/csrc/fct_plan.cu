@@ -445,7 +445,7 @@ extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *my
         return;
     const std::vector<int> *list = *which == 1 ? &d.boundary : (*which == 2 ? &d.interior : nullptr);
     WarpTilesHost h;
-    const int P = (*nl + 1) & ~1;
+    const int P = (*nl + 7) & ~7;
     if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, list, *tile_nodes, *smem_cap, h)) {
         *istat = 2;   // mesh not eligible
         return;

@@ -108,19 +108,49 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         : "memory");
 }
 
+// producer-side wait: backs off between probes so that an idle producer warp does not compete
+// with the consumers for issue slots
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
+
 __device__ __forceinline__ double flip_sign(double v, unsigned sgn)
 {
     return __hiloint2double(__double2hiint(v) ^ (int)sgn, __double2loint(v));
 }
 
-// a / b exactly as IEEE division; a zero numerator over a normal denominator (a local extremum:
-// bound == low-order value, very common) skips the division's slow path: (+-0) * b has the sign
-// and value of (+-0) / b.
-__device__ __forceinline__ double div_exact(double a, double b)
+// min(1, a / b) with a / b exactly the IEEE quotient.  A zero numerator (a local extremum: bound ==
+// low-order value, a quarter of all cells) would send the compiler's division into its slow path
+// on almost every warp; branch-free detour: q = (a == 0 ? 1 : a) / b, and for a == 0 the result
+// (+-0) * (1 / b) has the value and sign of (+-0) / b for every b (0 * inf = NaN = 0 / 0 included).
+__device__ __forceinline__ double limit_quotient(double a, double b)
 {
-    const unsigned eb = (unsigned)__double2hiint(b) & 0x7ff00000u;
-    if (a == 0. && eb != 0u && eb != 0x7ff00000u) return a * b;
-    return a / b;
+    const bool z = a == 0.;
+    const double q = (z ? 1. : a) / b;
+    const double r = z ? a * q : q;
+    double o;
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.lt.f64 p, %1, 0d3FF0000000000000;\n"
+        "selp.f64 %0, %1, 0d3FF0000000000000, p;\n"
+        "}"
+        : "=d"(o)
+        : "d"(r));
+    return o;
 }
 
 
@@ -130,18 +160,23 @@ __device__ __forceinline__ double div_exact(double a, double b)
 
 // One edge of phase A for two levels z0, z0+1.  meta = depth | writer << 30 | second << 31.
 //   bounds: hi = pick_max(hi, x), lw = pick_min(lw, y) for levels above the edge depth
-//   b1 horizontal (reference.cpp:417-423): q = +-h;  p += max(0, q);  m += min(0, q)
-//   (adding +0 is exact and p, m never are -0, so the sums are predicated DADDs)
+//   b1 horizontal (reference.cpp:417-423): q = +-h;  p += max(0, q);  m += min(0, q), written for
+//   the (idle) FP64 pipe instead of compare + select on the (busy) ALU pipe:
+//     max(0, q) = (q + |q|) / 2 and min(0, q) = (q - |q|) / 2 exactly, q = h * s with s = +-1, so
+//     p = fma(fma(h, s, |h|), 0.5, p) rounds once, to the same value as p + max(0, q); a
+//     non-positive q adds +0, which changes neither p >= +0 nor m <= +0.
 __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, const double2 &y, const double2 &h,
                                           double &hi0, double &hi1, double &lw0, double &lw1, double &p0,
                                           double &p1, double &m0, double &m1)
 {
     asm("{\n"
         ".reg .pred P0, P1, q;\n"
-        ".reg .b32 dg, sg, a, b, z1;\n"
-        ".reg .f64 t;\n"
+        ".reg .b32 dg, sh, z1;\n"
+        ".reg .f64 s, a, t;\n"
         "and.b32 dg, %9, 0xffff;\n"
-        "and.b32 sg, %9, 0x80000000;\n"
+        "and.b32 sh, %9, 0x80000000;\n"
+        "or.b32 sh, sh, 0x3FF00000;\n"
+        "mov.b64 s, {0, sh};\n"
         "add.s32 z1, %8, 1;\n"
         "setp.lt.s32 P0, %8, dg;\n"
         "setp.lt.s32 P1, z1, dg;\n"
@@ -153,23 +188,35 @@ __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, co
         "selp.f64 %2, %12, %2, q;\n"
         "setp.lt.and.f64 q, %13, %3, P1;\n"
         "selp.f64 %3, %13, %3, q;\n"
-        "mov.b64 {a, b}, %14;\n"
-        "xor.b32 b, b, sg;\n"
-        "mov.b64 t, {a, b};\n"
-        "setp.gt.and.f64 q, t, 0d0000000000000000, P0;\n"
-        "@q add.rn.f64 %4, %4, t;\n"
-        "setp.lt.and.f64 q, t, 0d0000000000000000, P0;\n"
-        "@q add.rn.f64 %6, %6, t;\n"
-        "mov.b64 {a, b}, %15;\n"
-        "xor.b32 b, b, sg;\n"
-        "mov.b64 t, {a, b};\n"
-        "setp.gt.and.f64 q, t, 0d0000000000000000, P1;\n"
-        "@q add.rn.f64 %5, %5, t;\n"
-        "setp.lt.and.f64 q, t, 0d0000000000000000, P1;\n"
-        "@q add.rn.f64 %7, %7, t;\n"
+        "abs.f64 a, %14;\n"
+        "fma.rn.f64 t, %14, s, a;\n"
+        "@P0 fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
+        "neg.f64 a, a;\n"
+        "fma.rn.f64 t, %14, s, a;\n"
+        "@P0 fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
+        "abs.f64 a, %15;\n"
+        "fma.rn.f64 t, %15, s, a;\n"
+        "@P1 fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
+        "neg.f64 a, a;\n"
+        "fma.rn.f64 t, %15, s, a;\n"
+        "@P1 fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
         "}"
         : "+d"(hi0), "+d"(hi1), "+d"(lw0), "+d"(lw1), "+d"(p0), "+d"(p1), "+d"(m0), "+d"(m1)
         : "r"(z0), "r"(meta), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y), "d"(h.x), "d"(h.y));
+}
+
+// store two consecutive levels, or only the first when the column ends between them (one
+// predicated pair instead of two divergent code paths)
+__device__ __forceinline__ void wt_store2(double *p, double a, double b, bool both)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred f;\n"
+        "setp.ne.s32 f, %3, 0;\n"
+        "@f st.global.v2.f64 [%0], {%1, %2};\n"
+        "@!f st.global.f64 [%0], %1;\n"
+        "}" ::"l"(p), "d"(a), "d"(b), "r"((int)both)
+        : "memory");
 }
 
 // b1 vertical of two levels (reference.cpp:397-398): p = max(0, f[z]) + max(0, -f[z+1]),
@@ -406,26 +453,16 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
     bm1 -= l1;
     bn1 -= l1;
     // ---- b2, reference.cpp:432-435 ----
-    double flux = p0 * A.dt * ai0 + A.eps;
-    const double pf0 = pick_min(1., div_exact(bm0, flux));
-    flux = m0 * A.dt * ai0 - A.eps;
-    const double mf0 = pick_min(1., div_exact(bn0, flux));
-    flux = p1 * A.dt * ai1 + A.eps;
-    const double pf1 = pick_min(1., div_exact(bm1, flux));
-    flux = m1 * A.dt * ai1 - A.eps;
-    const double mf1 = pick_min(1., div_exact(bn1, flux));
+    const double pf0 = limit_quotient(bm0, p0 * A.dt * ai0 + A.eps);
+    const double mf0 = limit_quotient(bn0, m0 * A.dt * ai0 - A.eps);
+    const double pf1 = limit_quotient(bm1, p1 * A.dt * ai1 + A.eps);
+    const double mf1 = limit_quotient(bn1, m1 * A.dt * ai1 - A.eps);
     const size_t off = tn + I.grow;
-    if (z0 + 1 < nz) {
-        *reinterpret_cast<double2 *>(A.ttf_max + off) = make_double2(bm0, bm1);
-        *reinterpret_cast<double2 *>(A.ttf_min + off) = make_double2(bn0, bn1);
-        *reinterpret_cast<double2 *>(A.plus + off) = make_double2(pf0, pf1);
-        *reinterpret_cast<double2 *>(A.minus + off) = make_double2(mf0, mf1);
-    } else {
-        A.ttf_max[off] = bm0;
-        A.ttf_min[off] = bn0;
-        A.plus[off] = pf0;
-        A.minus[off] = mf0;
-    }
+    const bool both = z0 + 1 < nz;
+    wt_store2(A.ttf_max + off, bm0, bm1, both);
+    wt_store2(A.ttf_min + off, bn0, bn1, both);
+    wt_store2(A.plus + off, pf0, pf1, both);
+    wt_store2(A.minus + off, mf0, mf1, both);
 }
 
 // ---- phase B: one warp item ------------------------------------------------------------------------
@@ -504,24 +541,15 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
         double hl0, hl1;
         wt_edge_b(z0, e.z, po, mo, h, pp.x, pp.y, mm.x, mm.y, ar0, ar1, dh0, dh1, hl0, hl1);
         const int dg = e.z & 0xffff;
-        if ((e.z & 0x40000000) && z0 < dg) {
-            double *o = g_ho + (unsigned)e.w + z0;
-            if (z0 + 1 < dg) *reinterpret_cast<double2 *>(o) = make_double2(hl0, hl1);
-            else o[0] = hl0;
-        }
+        if ((e.z & 0x40000000) && z0 < dg) wt_store2(g_ho + (unsigned)e.w + z0, hl0, hl1, z0 + 1 < dg);
     }
     // ---- c vertical, docs/refactoring.md:295-300 ----
     const double dv0 = q_dv.x - q_t.x * q_hn.x + q_l.x * q_hw.x + (fl0 - fl1) * ar0;
     const double dv1 = q_dv.y - q_t.y * q_hn.y + q_l.y * q_hw.y + (fl1 - fl2) * ar1;
-    if (z0 + 1 < nz) {
-        *reinterpret_cast<double2 *>(g_vout + I.grow) = make_double2(fl0, fl1);
-        *reinterpret_cast<double2 *>(A.del_v + off) = make_double2(dv0, dv1);
-        *reinterpret_cast<double2 *>(A.del_h + off) = make_double2(dh0, dh1);
-    } else {
-        g_vout[I.grow] = fl0;
-        A.del_v[off] = dv0;
-        A.del_h[off] = dh0;
-    }
+    const bool both = z0 + 1 < nz;
+    wt_store2(g_vout + I.grow, fl0, fl1, both);
+    wt_store2(A.del_v + off, dv0, dv1, both);
+    wt_store2(A.del_h + off, dh0, dh1, both);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -531,7 +559,7 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
 // ------------------------------------------------------------------------------------------------
 template <bool PHASE_A, int NSTAGE, int NWC, int NPW>
 __global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? 1 : 0) + NWC) * 32, 1)
-k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes)
+k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
     extern __shared__ __align__(128) unsigned char wt_sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -542,7 +570,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes)
     auto b_rows = [&](int s) { return bar + 8u * (2 * NSTAGE + s); };
     auto b_ready = [&](int s) { return bar + 8u * (3 * NSTAGE + s); };
     int *next_item = reinterpret_cast<int *>(wt_sm + 8 * 4 * NSTAGE);
-    static_assert(8 * 4 * NSTAGE + 4 * NSTAGE <= WT_SMEM_HEAD, "smem head");
+    int *tile_of = next_item + NSTAGE;   // (tile, tracer) index staged in each stage, -1: no more work
+    static_assert(8 * 4 * NSTAGE + 8 * NSTAGE <= WT_SMEM_HEAD, "smem head");
     const int total = T.ntiles * ntracers;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -556,27 +585,48 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes)
     __syncthreads();
 
     if (warp == 0) {
-        // ---- blob fetcher: refills a stage as soon as every consumer warp has left it ----
-        int it = 0;
-        for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+        // ---- blob fetcher: refills a stage as soon as every consumer warp has left it.  Tiles are
+        // drawn from a device-wide counter, so the CTAs work through the space-filling curve in
+        // order: the tiles in flight stay a compact patch whose halo rows hit L2, and no SM idles at
+        // the end.  (sched_ctr == nullptr: static round-robin.) ----
+        for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
-            mbar_wait(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+            int v = 0;
+            if (lane == 0) v = sched_ctr ? atomicAdd(sched_ctr, 1) : (int)(blockIdx.x + (unsigned)it * gridDim.x);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v >= total) {
+                if (lane == 0) {
+                    tile_of[s] = -1;
+                    mbar_arrive(b_blob(s));
+                }
+                break;
+            }
             if (lane == 0) {
                 const int tile = v % T.ntiles;
                 const unsigned b0 = __ldg(T.blob_off + tile), b1 = __ldg(T.blob_off + tile + 1);
                 next_item[s] = 0;
+                tile_of[s] = v;
                 mbar_expect_tx(b_blob(s), (b1 - b0) * 16u);
                 bulk_g2s(smem_u32(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes), T.blob + b0, (b1 - b0) * 16u, b_blob(s));
             }
             __syncwarp();
         }
+        // the last CTA to finish drawing rearms the counter for the next launch
+        if (sched_ctr && lane == 0) {
+            if (atomicAdd(sched_ctr + 1, 1) == (int)gridDim.x - 1) {
+                sched_ctr[0] = 0;
+                sched_ctr[1] = 0;
+            }
+        }
     } else if (warp <= NPW) {
         // ---- copy issuers: one bulk copy per staged row, the list shared by NPW warps ----
-        int it = 0;
-        for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
+            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1);
+            const int v = tile_of[s];
+            if (v < 0) break;
             const int tr = v / T.ntiles;
-            mbar_wait(b_blob(s), (it / NSTAGE) & 1);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             // the transaction count may run negative until this arrives; the phase cannot complete before
             if (warp == 1 && lane == 0) mbar_expect_tx(b_rows(s), (uint32_t)V.tx_bytes);
@@ -595,25 +645,23 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes)
         }
     } else if (PHASE_A && warp == NPW + 1) {
         // ---- phase A: a1 in place on the landed rows, (fct_LO, ttf) -> (max, min), reference.cpp:315-316 ----
-        {
-            int it = 0;
-            for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
-                const int s = it % NSTAGE;
-                mbar_wait(b_blob(s), (it / NSTAGE) & 1);
-                const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
-                mbar_wait(b_rows(s), (it / NSTAGE) & 1);
-                double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
-                const int n16 = V.rows_bytes >> 4;
+        for (int it = 0;; ++it) {
+            const int s = it % NSTAGE;
+            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1);
+            if (tile_of[s] < 0) break;
+            const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
+            mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1);
+            double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
+            const int n16 = V.rows_bytes >> 4;
 #pragma unroll 4
-                for (int g = lane; g < n16; g += 32) {
-                    const double2 l = pa[g], t = pb[g];
-                    pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
-                    pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));
-                }
-                fence_proxy_async();   // the next refill of this stage is written by the async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b_ready(s));
+            for (int g = lane; g < n16; g += 32) {
+                const double2 l = pa[g], t = pb[g];
+                pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
+                pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));
             }
+            fence_proxy_async();   // the next refill of this stage is written by the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_ready(s));
         }
     } else {
         // ---- consumers ----
@@ -622,24 +670,29 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes)
             if (lane == 0) wi = atomicAdd(next_item + s, 1);
             return __shfl_sync(0xffffffffu, wi, 0);
         };
-        int it = 0;
-        for (int v = blockIdx.x; v < total; v += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
+            mbar_wait(b_blob(s), (it / NSTAGE) & 1);
+            const int v = tile_of[s];
+            if (v < 0) break;
             const int tr = v / T.ntiles;
             mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             const size_t tn = tr * A.ts_node;
             const double *g_v = A.adf_v + tr * A.ts_nodev;
-            int wi = grab(s);
+            // two items ahead: the index after next is drawn (shared atomic + shuffle) and the next
+            // item's first-needed values are loaded while the current item is computed
+            int wi = grab(s), wn = grab(s);
             WtEarly E;
             if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v);
             while (wi < V.n_witems) {
-                const int wn = grab(s);
                 WtEarly En;
                 if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v);
+                const int wnn = grab(s);
                 if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, E);
                 else wt_item_b(A, V, wi, lane, tn, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E);
                 wi = wn;
+                wn = wnn;
                 E = En;
             }
             __syncwarp();

@@ -164,6 +164,9 @@ class DevicePlan:
         p = C.c_int()
         self.lib.fct_ale_plan_pitch_(C.byref(self.h), C.byref(p))
         self.pitch = p.value
+        wt, tt = C.c_int(), C.c_int()
+        self.lib.fct_ale_plan_kernels_(C.byref(self.h), C.byref(wt), C.byref(tt))
+        self.kernels = "warp" if wt.value else ("tile" if tt.value else "untiled")
 
     def free(self):
         st = C.c_int()
@@ -279,6 +282,26 @@ class DeviceFields:
         if sync:
             self.stream.sync()
         return st.value
+
+    # the arrays that change every tracer step (hnode / hnode_new move with the ALE surface) and the
+    # results FESOM2 consumes after fct_ale (the advective tendencies, docs/refactoring.md:292-314)
+    STEP_INPUTS = ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "hnode", "hnode_new", "del_ttf_advvert",
+                   "del_ttf_advhoriz")
+    STEP_RESULTS = ("del_ttf_advvert", "del_ttf_advhoriz")
+
+    def host_step(self, f: Fields, out: Fields, mode: int = 1, halo: Optional[HaloLink] = None, tracer: int = 0) -> int:
+        """One end-to-end tracer step for a caller whose fields live on the HOST: upload this step's
+        inputs from `f`, run a1..c on the device, download the tendencies into `out`, wait."""
+        for k in self.STEP_INPUTS:
+            self.upload_field(k, getattr(f, k), tracer)
+        st = self.step(f, mode=mode, halo=halo, sync=False)
+        for k in self.STEP_RESULTS:
+            self.download_field(k, getattr(out, k), tracer)
+        self.stream.sync()
+        return st
+
+    def host_step_bytes(self, f: Fields):
+        return (sum(getattr(f, k).nbytes for k in self.STEP_INPUTS), sum(getattr(f, k).nbytes for k in self.STEP_RESULTS))
 
     def stage(self, name: str, f: Fields, sync: bool = True):
         st = C.c_int()

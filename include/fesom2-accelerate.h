@@ -198,7 +198,11 @@ void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D,
                            int *edges, int *edge_tri, int *tile_nodes, int *smem_cap,
                            int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
                            unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat);
-/* pitch (in doubles) of every padded device row of this plan: nl rounded up to an even count */
+/* which fused kernels *mode 1 of fct_ale_step_ will run on this plan: the persistent TMA-staged
+ * warp-item kernels (*warp_tiles), else the tile-staged ones (*staged_tiles), else the untiled */
+void fct_ale_plan_kernels_(void **plan, int *warp_tiles, int *staged_tiles);
+/* pitch (in doubles) of every padded device row of this plan: nl rounded up to a multiple of 8
+ * (64 bytes), so that no DRAM sector is shared by two rows */
 void fct_ale_plan_pitch_(void **plan, int *pitch);
 
 /* Device arrays for a batch of *ntracers tracers on a plan, rows padded to the plan pitch.

@@ -68,7 +68,7 @@ def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
     want = f.copy()
     oracle_mod.fct_ale(m, want)
     plan = harness.DevicePlan(m)
-    assert plan.pitch % 2 == 0 and plan.pitch >= m.nl
+    assert plan.pitch % 8 == 0 and plan.pitch >= m.nl
     df = harness.DeviceFields(plan, 1, with_uv=True)
     df.upload(f)
     assert df.step(f, mode=mode) == 10

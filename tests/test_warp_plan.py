@@ -84,7 +84,7 @@ def pad(a, P):
 
 def emulate(m, f, blob, off, ntiles):
     """Both fused phases on the padded layout; returns the dict of padded result arrays."""
-    P = (m.nl + 1) & ~1
+    P = (m.nl + 7) & ~7
     L = m.L
     g = {k: pad(getattr(f, k), P) for k in ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area", "area_inv", "hnode",
                                             "hnode_new", "del_ttf_advvert", "del_ttf_advhoriz", "fct_ttf_max",
@@ -294,7 +294,7 @@ def test_deep_columns_are_cut_with_ghost_slots(mesh_mod, abi, oracle_mod):
     st, nt, smem, blob, off = inspect(abi, m, 64, 74 * 1024)
     assert st == 0 and smem <= 74 * 1024
     ghosts = 0
-    P = (m.nl + 1) & ~1
+    P = (m.nl + 7) & ~7
     for t in range(nt):
         T = Tile(blob[off[t] * 4: off[t + 1] * 4], P)
         live = T.sched[T.sched != 0xffff]

@@ -11,7 +11,7 @@ nx, ny, nl = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "400x317x48
 cfgs = [tuple(int(v) for v in c.split(":")) for c in (sys.argv[2] if len(sys.argv) > 2 else "0:0:3:0:0:0").split(",")]
 reps = 10
 m = mesh.make_mesh(nx, ny, nl)
-f = mesh.make_fields(m, with_uv=False, poison=False)
+f = mesh.fast_fields(m) if m.myDim_nod2D > 500000 else mesh.make_fields(m, with_uv=False, poison=False)
 Sn, Sg = m.S_n(), m.S_g()
 algA, algB = 8 * (8 * Sn + Sg) + 16 * m.myDim_nod2D, 8 * (13 * Sn + 2 * Sg)
 print(f"N={m.myDim_nod2D} nl={nl} S_n={Sn} S_g={Sg}", flush=True)
