@@ -318,9 +318,9 @@ struct WarpVariant {
 #define WT_VA(S, C, I) {k_phase_warp<true, S, C, I>, true, S, C, I}
 #define WT_VB(S, C, I) {k_phase_warp<false, S, C, I>, false, S, C, I}
 static const WarpVariant g_wvariants[] = {
-    WT_VA(3, 18, 4), WT_VA(3, 14, 4), WT_VA(3, 16, 6), WT_VA(3, 10, 4), WT_VA(3, 20, 2),
+    WT_VA(3, 18, 4), WT_VA(3, 14, 4), WT_VA(3, 16, 6), WT_VA(3, 10, 4), WT_VA(3, 20, 2), WT_VA(3, 22, 4), WT_VA(3, 26, 4), WT_VA(3, 20, 6),
     WT_VA(2, 18, 4), WT_VA(2, 14, 4), WT_VA(2, 16, 6), WT_VA(2, 10, 4), WT_VA(2, 20, 2),
-    WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 13, 2), WT_VB(3, 19, 4), WT_VB(3, 13, 6),
+    WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 13, 2), WT_VB(3, 19, 4), WT_VB(3, 13, 6), WT_VB(3, 23, 4), WT_VB(3, 27, 4), WT_VB(3, 17, 6),
     WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(2, 13, 2), WT_VB(2, 19, 4), WT_VB(2, 13, 6),
 };
 
@@ -344,7 +344,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     }
     // consumer / issuer warps: the closest compiled variant (0: default)
     int nwc = env_int(isA ? "FCT_WT_WARPS_A" : "FCT_WT_WARPS_B", 0), npw = env_int("FCT_WT_ISSUERS", 0);
-    nwc = nwc <= 0 ? (isA ? 18 : 11) : nwc;   // phase B needs ~110 registers: 16 warps in all
+    nwc = nwc <= 0 ? (isA ? 18 : 19) : nwc;   // 24 warps in all at 80 registers
     npw = npw <= 0 ? 4 : npw;
     constexpr int NV = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     int vi = -1, best = 1 << 30;

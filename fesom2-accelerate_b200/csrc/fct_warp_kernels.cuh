@@ -37,6 +37,7 @@
 #include <cstdint>
 
 #include "fct_kernels.cuh"
+#include "fct_tile_kernels.cuh"   // prefetch_l2
 
 namespace fct {
 
@@ -368,7 +369,7 @@ struct WtEarly {
     double f0, f1, f2, a0, a1;
 };
 template <bool PHASE_A>
-__device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, int wi, int lane, const double *g_v)
+__device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, int wi, int lane, const double *g_v, size_t tn)
 {
     WtEarly E;
     E.f0 = E.f1 = E.f2 = 0.;
@@ -386,6 +387,16 @@ __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, in
             const double2 aa = __ldg(reinterpret_cast<const double2 *>(A.area + grow));
             E.a0 = aa.x;
             E.a1 = aa.y;
+            // the operands of c vertical are consumed after the item's edge loop: pull them into L2
+            // now (one probe per 64 bytes) instead of holding 24 registers for loads in flight
+            if ((z0 & 7) == 0) {
+                prefetch_l2(A.del_v + tn + grow);
+                prefetch_l2(A.del_h + tn + grow);
+                prefetch_l2(A.ttf + tn + grow);
+                prefetch_l2(A.lo + tn + grow);
+                prefetch_l2(A.hnode + grow);
+                prefetch_l2(A.hnode_new + grow);
+            }
         }
     }
     return E;
@@ -473,13 +484,7 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
     if (!I.out) return;   // ghost slots exist for phase A's stencil only
     const int z0 = I.z0, nz = I.nz;
     const size_t off = tn + I.grow;
-    // ---- the own column's loads for c vertical: used after the edge loop ----
-    const double2 q_dv = *reinterpret_cast<const double2 *>(A.del_v + off);
     const double2 q_dh = *reinterpret_cast<const double2 *>(A.del_h + off);
-    const double2 q_t = __ldg(reinterpret_cast<const double2 *>(A.ttf + off));
-    const double2 q_l = __ldg(reinterpret_cast<const double2 *>(A.lo + off));
-    const double2 q_hn = __ldg(reinterpret_cast<const double2 *>(A.hnode + I.grow));
-    const double2 q_hw = __ldg(reinterpret_cast<const double2 *>(A.hnode_new + I.grow));
     // own factors from the staged rows: levels z0-1 .. z0+2
     const unsigned char *pr = I.ra + I.own, *mr = I.rb + I.own;
     const double2 pp = *reinterpret_cast<const double2 *>(pr);
@@ -543,7 +548,12 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
         const int dg = e.z & 0xffff;
         if ((e.z & 0x40000000) && z0 < dg) wt_store2(g_ho + (unsigned)e.w + z0, hl0, hl1, z0 + 1 < dg);
     }
-    // ---- c vertical, docs/refactoring.md:295-300 ----
+    // ---- c vertical, docs/refactoring.md:295-300 (operands prefetched into L2 one item ahead) ----
+    const double2 q_dv = *reinterpret_cast<const double2 *>(A.del_v + off);
+    const double2 q_t = __ldg(reinterpret_cast<const double2 *>(A.ttf + off));
+    const double2 q_l = __ldg(reinterpret_cast<const double2 *>(A.lo + off));
+    const double2 q_hn = __ldg(reinterpret_cast<const double2 *>(A.hnode + I.grow));
+    const double2 q_hw = __ldg(reinterpret_cast<const double2 *>(A.hnode_new + I.grow));
     const double dv0 = q_dv.x - q_t.x * q_hn.x + q_l.x * q_hw.x + (fl0 - fl1) * ar0;
     const double dv1 = q_dv.y - q_t.y * q_hn.y + q_l.y * q_hw.y + (fl1 - fl2) * ar1;
     const bool both = z0 + 1 < nz;
@@ -684,10 +694,10 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             // item's first-needed values are loaded while the current item is computed
             int wi = grab(s), wn = grab(s);
             WtEarly E;
-            if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v);
+            if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v, tn);
             while (wi < V.n_witems) {
                 WtEarly En;
-                if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v);
+                if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v, tn);
                 const int wnn = grab(s);
                 if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, E);
                 else wt_item_b(A, V, wi, lane, tn, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E);
