@@ -267,7 +267,7 @@ static void build_plan_tiles(Plan *p, const DerivedHost &d, const int *nlev_n)
 }
 
 // ---- warp-item kernels: plan tables, launch ---------------------------------------------------
-static int wt_stages() { return std::min(std::max(env_int("FCT_WT_STAGES", 3), 2), 3); }
+static int wt_stages() { return std::min(std::max(env_int("FCT_WT_STAGES", 3), 2), 4); }
 // one stage of the ring: an equal share of the 227 KB a CTA may own
 static int wt_stage_cap(int stages) { return ((WT_SMEM_MAX - WT_SMEM_HEAD) / stages) & ~127; }
 
@@ -318,11 +318,12 @@ struct WarpVariant {
 #define WT_VA(S, C, I) {k_phase_warp<true, S, C, I>, true, S, C, I}
 #define WT_VB(S, C, I) {k_phase_warp<false, S, C, I>, false, S, C, I}
 static const WarpVariant g_wvariants[] = {
-    WT_VA(3, 18, 4), WT_VA(3, 14, 4), WT_VA(3, 16, 6), WT_VA(3, 10, 4), WT_VA(3, 20, 2), WT_VA(3, 22, 4), WT_VA(3, 26, 4), WT_VA(3, 20, 6),
-    WT_VA(2, 18, 4), WT_VA(2, 14, 4), WT_VA(2, 16, 6), WT_VA(2, 10, 4), WT_VA(2, 20, 2),
-    WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 13, 2), WT_VB(3, 19, 4), WT_VB(3, 13, 6), WT_VB(3, 23, 4), WT_VB(3, 27, 4), WT_VB(3, 17, 6),
-    WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(2, 13, 2), WT_VB(2, 19, 4), WT_VB(2, 13, 6),
+    WT_VA(3, 17, 4), WT_VA(3, 13, 4), WT_VA(3, 15, 6), WT_VA(3, 9, 4), WT_VA(3, 19, 2),
+    WT_VA(2, 17, 4), WT_VA(2, 13, 4), WT_VA(2, 15, 6), WT_VA(4, 17, 4), WT_VA(4, 15, 6),
+    WT_VB(3, 19, 4), WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 17, 6), WT_VB(3, 21, 2),
+    WT_VB(2, 19, 4), WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(4, 19, 4), WT_VB(4, 17, 6),
 };
+
 
 // which: 0 all owned nodes, 1 boundary list, 2 interior list
 bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s)
@@ -338,13 +339,14 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // as deep a ring as the tiles of this plan admit
     int stages = wt_stages();
     while (stages > 2 && WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) --stages;
+    if (stages == 4 && env_int("FCT_WT_STAGES", 3) != 4) stages = 3;
     if (WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) {
         std::fprintf(stderr, "fesom2-accelerate: warp tiles of %d B do not fit two stages\n", stage_bytes);
         return false;
     }
     // consumer / issuer warps: the closest compiled variant (0: default)
     int nwc = env_int(isA ? "FCT_WT_WARPS_A" : "FCT_WT_WARPS_B", 0), npw = env_int("FCT_WT_ISSUERS", 0);
-    nwc = nwc <= 0 ? (isA ? 18 : 19) : nwc;   // 24 warps in all at 80 registers
+    nwc = nwc <= 0 ? (isA ? 17 : 19) : nwc;   // 24 warps in all at 80 registers
     npw = npw <= 0 ? 4 : npw;
     constexpr int NV = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     int vi = -1, best = 1 << 30;
@@ -398,7 +400,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         ctr = ctr_ring + 2 * (ctr_next.fetch_add(1) % CTR_SLOTS);
     }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
-    v.fn<<<grid, (v.issuers + 1 + (isA ? 1 : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
+    v.fn<<<grid, (v.issuers + 1 + (isA ? WT_CONVERTERS : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");
 }

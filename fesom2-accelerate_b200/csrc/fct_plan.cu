@@ -197,7 +197,7 @@ namespace {
 struct StagedRow {
     unsigned goff;   // global element offset of the row
     int soff;        // byte offset inside its staging region
-    int bytes;
+    int bytes;       // bytes copied
 };
 inline int pad16(int b) { return (b + 15) & ~15; }
 inline int row_bytes(int levels) { return ((std::max(levels, 0) + 1) & ~1) * 8; }
@@ -247,13 +247,14 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
     const int slack = P * 8 + 32;   // masked lanes read up to one row past the last staged byte
     std::vector<int> nstamp((size_t)NT, -1), nsoff((size_t)NT, 0), estamp((size_t)std::max(G, 1), -1), esoff((size_t)std::max(G, 1), 0);
     std::vector<StagedRow> rows, erows;
+    std::vector<unsigned> gaps;   // (first double of the edge region | doubles << 16) to zero in phase A
     std::vector<int4> hdr, ent;
     std::vector<unsigned short> sched;
     std::vector<std::pair<int, int>> a, b;
     std::vector<char> checked((size_t)N, 0);
 
     auto need_bytes = [&](size_t nrows, size_t nerows, size_t nn, size_t nent, size_t nsched, int rb, int eb) {
-        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + nn * 16 + nent * 16 +
+        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + pad16((int)nerows * 4) + nn * 16 + nent * 16 +
                             pad16((int)((nsched + W - 1) / W * W) * 2);
         return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack;
     };
@@ -262,6 +263,7 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
     while (pos < count) {
         rows.clear();
         erows.clear();
+        gaps.clear();
         hdr.clear();
         ent.clear();
         sched.clear();
@@ -310,7 +312,7 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
                     ++add_rows;
                 }
                 if (estamp[g] != tile) {
-                    add_eb += row_bytes(FCT_META_DEPTH(d.edg[k].z));
+                    add_eb += row_bytes(std::max(nz, nlev_n[m] - 1));
                     ++add_erows;
                 }
             }
@@ -341,11 +343,16 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
                 const int4 e = d.edg[k];
                 const int other = touch(e.y);
                 if (estamp[e.x] != tile) {
+                    // the row's slot reaches down to the deeper of its two end columns; what the copy
+                    // does not deliver (levels below the edge depth, the pad level of an odd depth) is
+                    // zeroed by phase A's converter warp, so b1 horizontal needs no level mask
                     estamp[e.x] = tile;
                     esoff[e.x] = eb;
-                    const int bytes = row_bytes(FCT_META_DEPTH(e.z));
-                    erows.push_back({(unsigned)((long long)e.x * P), eb, bytes});
-                    eb += bytes;
+                    const int dg = FCT_META_DEPTH(e.z);
+                    const int slot = row_bytes(std::max(nz, nlev_n[e.y] - 1));
+                    erows.push_back({(unsigned)((long long)e.x * P), eb, row_bytes(dg)});
+                    if (slot / 8 > dg) gaps.push_back((unsigned)(eb / 8 + dg) | ((unsigned)(slot / 8 - dg) << 16));
+                    eb += slot;
                 }
                 const unsigned meta = (unsigned)FCT_META_DEPTH(e.z) | (FCT_META_WRITER(e.z) ? 0x40000000u : 0u) |
                                       (FCT_META_SECOND(e.z) ? 0x80000000u : 0u);
@@ -364,7 +371,8 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         // ---- assemble the blob ----
         const int off_rows = WT_HDR_BYTES;
         const int n_copies = 2 * (int)rows.size() + (int)erows.size();
-        const int off_hdr = off_rows + pad16(n_copies * 8);
+        const int off_gaps = off_rows + pad16(n_copies * 8);
+        const int off_hdr = off_gaps + pad16((int)gaps.size() * 4);
         const int off_ent = off_hdr + (int)hdr.size() * 16;
         const int off_sched = off_ent + (int)ent.size() * 16;
         const int blob_bytes = off_sched + pad16((int)sched.size() * 2);
@@ -386,6 +394,9 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         h[9] = rb;
         h[10] = eb;
         h[11] = (int)tx;
+        h[12] = (int)gaps.size();
+        h[13] = off_gaps;
+        if (!gaps.empty()) std::memcpy(buf.data() + off_gaps, gaps.data(), gaps.size() * 4);
         {
             // copy list: the rows of the three regions interleaved, so that the issuer warps (which
             // take consecutive 32-entry chunks) all touch every array; zero-length rows are dropped

@@ -50,12 +50,15 @@ struct WarpTilesDev {
 
 // warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A NPW+1 the a1 converter, then NWC consumers
 // (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128, 20 -> 96, 24 -> 80)
-constexpr int WT_SMEM_HEAD = 128;     // mbarriers + item counters in front of the stages
+constexpr int WT_SMEM_HEAD = 256;     // mbarriers + item counters in front of the stages
+constexpr int WT_CONVERTERS = 2;      // phase A: warps that turn the landed rows into the a1 bounds
 constexpr int WT_SMEM_MAX = 227 * 1024;
 // blob header: 16 ints
 //  [0] node rows  [1] edge rows  [2] nodes  [3] warp items
 //  [4] byte offset of the edge-row table  [5] of the node headers  [6] of the entries  [7] of the schedule
 //  [8] blob bytes  [9] bytes of ONE staged node-row region  [10] bytes of the edge-row region  [11] bytes the row copies deliver
+//  [12] gaps  [13] byte offset of the gap list: unsigned {first double in the edge region | doubles << 16}, the part of
+//       every edge-row slot no copy fills (phase A zeroes it: b1 horizontal then needs no level mask)
 // schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
 // node-row table at byte 64: int2 {global element offset of the row, (16-byte units) smem offset | size << 16}
 // node header int4: {node*pitch, nz | fillmin << 8 | self depth << 16, smem byte offset of the own row, first entry | entries << 16}
@@ -165,7 +168,8 @@ __device__ __forceinline__ double limit_quotient(double a, double b)
 //   the (idle) FP64 pipe instead of compare + select on the (busy) ALU pipe:
 //     max(0, q) = (q + |q|) / 2 and min(0, q) = (q - |q|) / 2 exactly, q = h * s with s = +-1, so
 //     p = fma(fma(h, s, |h|), 0.5, p) rounds once, to the same value as p + max(0, q); a
-//     non-positive q adds +0, which changes neither p >= +0 nor m <= +0.
+//     non-positive q adds +0, which changes neither p >= +0 nor m <= +0.  No level mask: below the
+//     edge depth the staged row holds zeros (the converter warp fills what no copy delivers).
 __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, const double2 &y, const double2 &h,
                                           double &hi0, double &hi1, double &lw0, double &lw1, double &p0,
                                           double &p1, double &m0, double &m1)
@@ -191,16 +195,16 @@ __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, co
         "selp.f64 %3, %13, %3, q;\n"
         "abs.f64 a, %14;\n"
         "fma.rn.f64 t, %14, s, a;\n"
-        "@P0 fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
+        "fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
         "neg.f64 a, a;\n"
         "fma.rn.f64 t, %14, s, a;\n"
-        "@P0 fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
+        "fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
         "abs.f64 a, %15;\n"
         "fma.rn.f64 t, %15, s, a;\n"
-        "@P1 fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
+        "fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
         "neg.f64 a, a;\n"
         "fma.rn.f64 t, %15, s, a;\n"
-        "@P1 fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
+        "fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
         "}"
         : "+d"(hi0), "+d"(hi1), "+d"(lw0), "+d"(lw1), "+d"(p0), "+d"(p1), "+d"(m0), "+d"(m1)
         : "r"(z0), "r"(meta), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y), "d"(h.x), "d"(h.y));
@@ -306,8 +310,9 @@ struct WtView {
     unsigned char *blob, *rowsA, *rowsB, *erows;
     const int4 *hdr, *ent;
     const unsigned short *sched;
-    int rows_bytes, erows_bytes, tx_bytes;
+    int rows_bytes, erows_bytes, tx_bytes, n_gaps;
     const int2 *copies;
+    const unsigned *gaps;
 };
 
 __device__ __forceinline__ WtView wt_view(unsigned char *stage)
@@ -317,6 +322,9 @@ __device__ __forceinline__ WtView wt_view(unsigned char *stage)
     const int4 h0 = reinterpret_cast<const int4 *>(stage)[0];
     const int4 h1 = reinterpret_cast<const int4 *>(stage)[1];
     const int4 h2 = reinterpret_cast<const int4 *>(stage)[2];
+    const int4 h3 = reinterpret_cast<const int4 *>(stage)[3];
+    v.n_gaps = h3.x;
+    v.gaps = reinterpret_cast<const unsigned *>(stage + h3.y);
     v.n_copies = h0.x;
     v.n_nodes = h0.z;
     v.n_witems = h0.w;
@@ -568,7 +576,7 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
 // dynamic smem: WT_SMEM_HEAD + NSTAGE * stage_bytes
 // ------------------------------------------------------------------------------------------------
 template <bool PHASE_A, int NSTAGE, int NWC, int NPW>
-__global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? 1 : 0) + NWC) * 32, 1)
+__global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0) + NWC) * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
     extern __shared__ __align__(128) unsigned char wt_sm[];
@@ -581,14 +589,14 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
     auto b_ready = [&](int s) { return bar + 8u * (3 * NSTAGE + s); };
     int *next_item = reinterpret_cast<int *>(wt_sm + 8 * 4 * NSTAGE);
     int *tile_of = next_item + NSTAGE;   // (tile, tracer) index staged in each stage, -1: no more work
-    static_assert(8 * 4 * NSTAGE + 8 * NSTAGE <= WT_SMEM_HEAD, "smem head");
+    static_assert(8 * 4 * NSTAGE + 8 * NSTAGE <= WT_SMEM_HEAD && NSTAGE <= 4, "smem head");
     const int total = T.ntiles * ntracers;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(b_empty(s), NWC);
             mbar_init(b_blob(s), 1);
             mbar_init(b_rows(s), 1);
-            mbar_init(b_ready(s), 1);
+            mbar_init(b_ready(s), WT_CONVERTERS);
         }
         fence_mbar_init();
     }
@@ -601,10 +609,15 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         // the end.  (sched_ctr == nullptr: static round-robin.) ----
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
-            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
-            int v = 0;
+            int v = 0;   // drawn before the wait: the device-wide atomic is off the refill's critical path
             if (lane == 0) v = sched_ctr ? atomicAdd(sched_ctr, 1) : (int)(blockIdx.x + (unsigned)it * gridDim.x);
             v = __shfl_sync(0xffffffffu, v, 0);
+            unsigned b0 = 0, b1 = 0;
+            if (lane == 0 && v < total) {
+                b0 = __ldg(T.blob_off + v % T.ntiles);
+                b1 = __ldg(T.blob_off + v % T.ntiles + 1);
+            }
+            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
             if (v >= total) {
                 if (lane == 0) {
                     tile_of[s] = -1;
@@ -613,8 +626,6 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 break;
             }
             if (lane == 0) {
-                const int tile = v % T.ntiles;
-                const unsigned b0 = __ldg(T.blob_off + tile), b1 = __ldg(T.blob_off + tile + 1);
                 next_item[s] = 0;
                 tile_of[s] = v;
                 mbar_expect_tx(b_blob(s), (b1 - b0) * 16u);
@@ -653,18 +664,24 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             }
             __syncwarp();
         }
-    } else if (PHASE_A && warp == NPW + 1) {
+    } else if (PHASE_A && warp <= NPW + WT_CONVERTERS) {
         // ---- phase A: a1 in place on the landed rows, (fct_LO, ttf) -> (max, min), reference.cpp:315-316 ----
+        const int cl = (warp - NPW - 1) * 32 + lane;   // lane among the converter warps
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
             mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1);
             if (tile_of[s] < 0) break;
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1);
+            for (int i = cl; i < V.n_gaps; i += 32 * WT_CONVERTERS) {
+                const unsigned g = V.gaps[i];
+                double *z = reinterpret_cast<double *>(V.erows) + (g & 0xffffu);
+                for (unsigned c = 0; c < (g >> 16); ++c) z[c] = 0.;
+            }
             double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
             const int n16 = V.rows_bytes >> 4;
 #pragma unroll 4
-            for (int g = lane; g < n16; g += 32) {
+            for (int g = cl; g < n16; g += 32 * WT_CONVERTERS) {
                 const double2 l = pa[g], t = pb[g];
                 pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
                 pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));

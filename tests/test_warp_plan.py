@@ -41,6 +41,8 @@ class Tile:
         h = np.frombuffer(b, np.int32, 16)
         (self.n_copies, self.n_erows, self.n_nodes, self.n_witems, self.n_rows, off_hdr, off_ent, off_sched,
          blob_bytes, self.rows_bytes, self.erows_bytes, self.tx) = [int(x) for x in h[:12]]
+        n_gaps, off_gaps = int(h[12]), int(h[13])
+        self.gaps = np.frombuffer(b, np.uint32, n_gaps, off_gaps)
         assert blob_bytes == len(b)
         self.copies = np.frombuffer(b, np.uint32, 2 * self.n_copies, 64).reshape(-1, 2)
         self.hdr = np.frombuffer(b, np.uint32, 4 * self.n_nodes, off_hdr).reshape(-1, 4)
@@ -99,6 +101,10 @@ def emulate(m, f, blob, off, ntiles):
             T = Tile(blob[off[t] * 4: off[t + 1] * 4], P)
             if phase == "A":
                 RA, RB, RE = T.stage(g["fct_LO"], g["ttf"], g["fct_adf_h"])
+                for gp in T.gaps:                                  # the converter warp's zero fill
+                    st, cnt = int(gp) & 0xffff, int(gp) >> 16
+                    assert cnt > 0 and st + cnt <= T.erows_bytes // 8
+                    RE[st:st + cnt] = 0.0
                 lo_, tt_ = RA.copy(), RB.copy()
                 with np.errstate(invalid="ignore"):
                     RA = np.where(lo_ < tt_, tt_, lo_)           # pick_max(lo, ttf)
@@ -164,14 +170,17 @@ def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
             ex, ey, ez, ew = [int(x) for x in T.ent[s["e0"] + k]]
             dg, second = ez & 0xffff, bool(ez >> 31)
             for v in range(2):
+                h = RE[ex // 8 + z0 + v]                          # b1 horizontal is NOT masked in the kernel
+                assert not np.isnan(h), "read of an edge-row byte that was neither staged nor zeroed"
+                assert z0 + v < dg or h == 0.0
+                q = -h if second else h
+                p[v] += pmax(0., q)
+                mm[v] += pmin(0., q)
                 if z0 + v < dg:
-                    x, y, h = RA[ey // 8 + z0 + v], RB[ey // 8 + z0 + v], RE[ex // 8 + z0 + v]
-                    assert not (np.isnan(x) or np.isnan(y) or np.isnan(h)), "read of a byte that was never staged"
+                    x, y = RA[ey // 8 + z0 + v], RB[ey // 8 + z0 + v]
+                    assert not (np.isnan(x) or np.isnan(y)), "read of a byte that was never staged"
                     hi[v] = pmax(hi[v], x)
                     lw[v] = pmin(lw[v], y)
-                    q = -h if second else h
-                    p[v] += pmax(0., q)
-                    mm[v] += pmin(0., q)
         s.update(hi=hi, lw=lw, p=p, m=mm)
         tv.append(s)
     for vl, s in enumerate(tv):
