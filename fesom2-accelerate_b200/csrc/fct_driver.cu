@@ -329,7 +329,8 @@ static const WarpVariant g_wvariants[] = {
 bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s)
 {
     const bool isA = stage == ST_PHASE_A;
-    const WarpTilesDev &T = p->wtiles[which];
+    WarpTilesDev T = p->wtiles[which];
+    T.diag = env_int("FCT_WT_DIAG", 0);
     if (T.ntiles <= 0) return true;
     if (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch) {
         std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");

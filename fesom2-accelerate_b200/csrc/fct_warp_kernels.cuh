@@ -46,6 +46,7 @@ struct WarpTilesDev {
     const unsigned *blob_off;   // [ntiles+1] in 16-byte units
     int ntiles;
     int smem_bytes;             // dynamic shared memory of one CTA (max over tiles)
+    int diag;                   // timing experiments only (wrong results): 1 skip the edge-row copies, 2 skip all row copies
 };
 
 // warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A NPW+1 the a1 converter, then NWC consumers
@@ -616,6 +617,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             if (lane == 0 && v < total) {
                 b0 = __ldg(T.blob_off + v % T.ntiles);
                 b1 = __ldg(T.blob_off + v % T.ntiles + 1);
+                // the stage is still busy: have the blob wait in L2
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(T.blob + b0), "r"((b1 - b0) * 16u) : "memory");
             }
             mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
             if (v >= total) {
@@ -650,7 +653,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             const int tr = v / T.ntiles;
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             // the transaction count may run negative until this arrives; the phase cannot complete before
-            if (warp == 1 && lane == 0) mbar_expect_tx(b_rows(s), (uint32_t)V.tx_bytes);
+            if (warp == 1 && lane == 0)
+                mbar_expect_tx(b_rows(s), T.diag == 0 ? (uint32_t)V.tx_bytes : (T.diag == 1 ? 2u * (uint32_t)V.rows_bytes : 0u));
             const double *ga = (PHASE_A ? A.lo : A.plus) + tr * A.ts_node;
             const double *gb = (PHASE_A ? A.ttf : A.minus) + tr * A.ts_node;
             const double *ge = A.adf_h_in + tr * A.ts_edge;
@@ -660,7 +664,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const uint32_t so = ((uint32_t)r.y & 0xffffu) << 4, sz = (((uint32_t)r.y >> 16) & 0xffu) << 4;
                 const uint32_t arr = ((uint32_t)r.y >> 24) & 3u;
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
-                bulk_g2s(sa + so, src, sz, b_rows(s));
+                if (T.diag == 0 || (T.diag == 1 && arr != 2)) bulk_g2s(sa + so, src, sz, b_rows(s));
             }
             __syncwarp();
         }
