@@ -200,7 +200,8 @@ def run_product(args):
 
     # ---------------- value: device-resident fused step ----------------
     plan = harness.DevicePlan(m)
-    df = harness.DeviceFields(plan, 1, with_uv=False)
+    # the packed level storage is the fast path's own layout (plain triangulations)
+    df = harness.DeviceFields(plan, 1, with_uv=False, packed=(plan.kernels == "warp"))
     df.upload(f, outputs=False)
     halo = None
     if world > 1:
@@ -237,7 +238,7 @@ def run_product(args):
     algB = 8 * (13 * Sn + 2 * Sg)
     kern = {}
     suffix = {"warp": "_warp", "tile": "_tile", "untiled": ""}[plan.kernels]
-    mode_name = {"warp": "persistent TMA-staged warp-item fused phases A+B", "tile": "tile-staged fused phases A+B",
+    mode_name = {"warp": "persistent TMA-staged warp-item fused phases A+B, packed level storage", "tile": "tile-staged fused phases A+B",
                  "untiled": "untiled fused phases A+B"}[plan.kernels]
     if world == 1:
         for base, alg in (("phaseA", algA), ("phaseB", algB)):

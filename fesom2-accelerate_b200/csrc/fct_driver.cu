@@ -282,15 +282,24 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
     TN = TN <= 0 ? 96 : std::min(TN, 255);
     const std::vector<int> *lists[3] = {nullptr, &d.boundary, &d.interior};
     const int nsets = p->H > 0 ? 3 : 1;
+    for (int layout = 0; layout < 2; ++layout) {
+    const bool packed = layout == 1;
+    if (packed) {
+        packed_columns(d, nlev_n, p->N + p->H, p->G, p->ncol, p->ecol);
+        p->d_ncol = upload_vec(p, p->ncol);
+        p->d_ecol = upload_vec(p, p->ecol);
+        if (!p->d_ncol || !p->d_ecol) return;
+    }
     WarpTilesHost h[3];
     for (int s = 0; s < nsets; ++s) {
-        if (!build_warptiles(d, nlev_n, p->N, p->N + p->H, p->G, p->pitch, lists[s], TN, cap, h[s])) {
+        if (!build_warptiles(d, nlev_n, p->N, p->N + p->H, p->G, p->pitch, packed ? p->ncol.data() : nullptr,
+                             packed ? p->ecol.data() : nullptr, lists[s], TN, cap, h[s])) {
             if (verbose) std::fprintf(stderr, "fesom2-accelerate: mesh is not eligible for the warp-item kernels\n");
             return;
         }
     }
     for (int s = 0; s < nsets; ++s) {
-        WarpTilesDev &T = p->wtiles[s];
+        WarpTilesDev &T = packed ? p->wtiles_pk[s] : p->wtiles[s];
         T.blob = upload_vec(p, h[s].blob);
         T.blob_off = upload_vec(p, h[s].blob_off);
         T.ntiles = h[s].ntiles;
@@ -298,14 +307,17 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
         if (!T.blob || !T.blob_off) return;
         if (verbose && h[s].ntiles > 0)
             std::fprintf(stderr,
-                         "fesom2-accelerate: warp tiles[%d]: %d tiles, %.1f nodes/tile, %.2f staged rows/node, %.2f staged edge rows/node "
-                         "(%.2f edge uses/node), lane fill %.1f%%, %.0f B plan/node, %d B smem/stage\n",
-                         s, h[s].ntiles, (double)h[s].nodes / h[s].ntiles, (double)h[s].staged_rows / h[s].nodes,
-                         (double)h[s].staged_erows / h[s].nodes, (double)h[s].edge_uses / h[s].nodes,
+                         "fesom2-accelerate: %s warp tiles[%d]: %d tiles, %.1f nodes/tile, %.2f staged rows/node, %.2f staged edge rows/node "
+                         "(%.2f edge uses/node), %.1f bulk copies/tile, lane fill %.1f%%, %.0f B plan/node, %d B smem/stage\n",
+                         packed ? "packed" : "padded", s, h[s].ntiles, (double)h[s].nodes / h[s].ntiles,
+                         (double)h[s].staged_rows / h[s].nodes, (double)h[s].staged_erows / h[s].nodes,
+                         (double)h[s].edge_uses / h[s].nodes, (double)h[s].copies / h[s].ntiles,
                          100.0 * h[s].slots / std::max<long long>(h[s].lanes, 1), 16.0 * h[s].blob.size() / h[s].nodes,
                          h[s].smem_bytes);
     }
-    p->wtiles_ok = true;
+    if (packed) p->wtiles_pk_ok = true;
+    else p->wtiles_ok = true;
+    }
 }
 
 typedef void (*warp_kern_t)(Arrays, WarpTilesDev, int, int, int *);
@@ -329,10 +341,15 @@ static const WarpVariant g_wvariants[] = {
 bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s)
 {
     const bool isA = stage == ST_PHASE_A;
-    WarpTilesDev T = p->wtiles[which];
+    const bool packed = A.pitchL == 0;   // Arrays of a packed Fields object carry no pitch
+    if (packed ? !p->wtiles_pk_ok : !p->wtiles_ok) {
+        std::fprintf(stderr, "fesom2-accelerate: this plan has no warp-item tiles for this layout\n");
+        return false;
+    }
+    WarpTilesDev T = packed ? p->wtiles_pk[which] : p->wtiles[which];
     T.diag = env_int("FCT_WT_DIAG", 0);
     if (T.ntiles <= 0) return true;
-    if (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch) {
+    if (!packed && (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch)) {
         std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");
         return false;
     }

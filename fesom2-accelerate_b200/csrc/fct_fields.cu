@@ -100,6 +100,31 @@ __global__ void k_repack(double *__restrict__ dst, const double *__restrict__ sr
     }
 }
 
+// dense host rows (width W) <-> packed columns: row r owns device slots [col[r], col[r+1]); only the
+// levels that have a slot travel, a download fills the rest of the dense row with zeros
+__global__ void k_pack_columns(double *__restrict__ dst, const double *__restrict__ src, const unsigned *__restrict__ col,
+                               size_t rows, int W)
+{
+    const size_t n = rows * (size_t)W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (size_t)W;
+        const unsigned c = (unsigned)(i - r * (size_t)W);
+        const unsigned c0 = __ldg(col + r), c1 = __ldg(col + r + 1);
+        if (c < c1 - c0) dst[c0 + c] = src[i];
+    }
+}
+__global__ void k_unpack_columns(double *__restrict__ dst, const double *__restrict__ src, const unsigned *__restrict__ col,
+                                 size_t rows, int W)
+{
+    const size_t n = rows * (size_t)W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (size_t)W;
+        const unsigned c = (unsigned)(i - r * (size_t)W);
+        const unsigned c0 = __ldg(col + r), c1 = __ldg(col + r + 1);
+        dst[i] = (c < c1 - c0) ? src[c0 + c] : 0.;
+    }
+}
+
 static bool run_stage(Fields *f, const Arrays &A, int stage, const int *list, int first, int count, cudaStream_t s)
 {
     return launch_stage(stage, 2, A, f->plan->dev, list, first, count, f->T, s);
@@ -153,26 +178,32 @@ void fct_ale_plan_pitch_(void **plan, int *pitch)
     *pitch = p ? p->pitch : 0;
 }
 
-void fct_ale_fields_create_(void **fields, void **plan, int *ntracers, int *with_uv_rhs, int *istat)
+static void fields_create(void **fields, void **plan, int *ntracers, bool with_uv, bool packed, int *istat)
 {
     *fields = nullptr;
     *istat = 1;
     Plan *p = P_(plan);
     if (!p || *ntracers < 1) return;
+    if (packed && !p->wtiles_pk_ok) {
+        std::fprintf(stderr, "fesom2-accelerate: the packed level storage needs a plan with warp-item tiles\n");
+        return;
+    }
     Fields *f = new (std::nothrow) Fields;
     if (!f) return;
     f->plan = p;
     f->T = *ntracers;
-    f->P = p->pitch;
+    f->packed = packed;
+    f->P = packed ? 0 : p->pitch;
     f->rows = (size_t)p->N + p->H;
-    f->ts_node = f->rows * f->P;
-    f->ts_edge = (size_t)p->G * f->P;
+    f->ts_node = packed ? (size_t)p->ncol.back() : f->rows * f->P;
+    f->ts_edge = packed ? (size_t)p->ecol.back() : (size_t)p->G * f->P;
     f->ts_uv = (size_t)p->E * f->P;
     bool ok = true;
     for (int id = 0; id < FCT_FIELD_COUNT && ok; ++id) {
-        if (id == FCT_UV_RHS && !(with_uv_rhs && *with_uv_rhs)) continue;
+        if (id == FCT_UV_RHS && (!with_uv || packed)) continue;
         const FieldMeta m = meta_of(id);
         size_t n = field_rows(f, m.kind) * f->P * (m.per_tracer ? f->T : 1) * (id == FCT_UV_RHS ? 2 : 1);
+        if (packed) n = (m.kind == ROW_EDGE ? f->ts_edge : f->ts_node) * (m.per_tracer ? f->T : 1);
         n = n ? n : 1;
         ok = cuda_ok(cudaMalloc(&f->buf[id], n * sizeof(double)), "cudaMalloc(fields)") &&
              cuda_ok(cudaMemset(f->buf[id], 0, n * sizeof(double)), "cudaMemset(fields)");
@@ -185,6 +216,16 @@ void fct_ale_fields_create_(void **fields, void **plan, int *ntracers, int *with
     }
     *fields = f;
     *istat = 0;
+}
+
+void fct_ale_fields_create_(void **fields, void **plan, int *ntracers, int *with_uv_rhs, int *istat)
+{
+    fields_create(fields, plan, ntracers, with_uv_rhs && *with_uv_rhs, false, istat);
+}
+
+void fct_ale_fields_create_packed_(void **fields, void **plan, int *ntracers, int *istat)
+{
+    fields_create(fields, plan, ntracers, false, true, istat);
 }
 
 void fct_ale_fields_destroy_(void **fields, int *istat)
@@ -212,13 +253,14 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
     const size_t unit = (*field == FCT_UV_RHS) ? 2 : 1;
     const size_t width = (size_t)(f->plan->nl - m.width_minus) * unit * sizeof(double);
     const size_t pitch = (size_t)f->P * unit * sizeof(double);
-    double *d = f->buf[*field] + (size_t)t * rows * f->P * unit;
+    double *d = f->buf[*field] + (f->packed ? (size_t)t * (m.kind == ROW_EDGE ? f->ts_edge : f->ts_node)
+                                            : (size_t)t * rows * f->P * unit);
     if (rows == 0) {
         *istat = 0;
         return;
     }
     cudaStream_t st = S_(stream);
-    if (width == pitch) {
+    if (!f->packed && width == pitch) {
         cudaError_t e = up ? cudaMemcpyAsync(d, host, rows * pitch, cudaMemcpyHostToDevice, st)
                            : cudaMemcpyAsync(host, d, rows * pitch, cudaMemcpyDeviceToHost, st);
         *istat = cuda_ok(e, up ? "field upload" : "field download") ? 0 : 1;
@@ -248,15 +290,18 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
     const int threads = 256;
     const int blocks = (int)std::min<size_t>((need + threads - 1) / threads, (size_t)148 * 16);
     bool ok;
+    const unsigned *col = m.kind == ROW_EDGE ? f->plan->d_ecol : f->plan->d_ncol;
     if (up) {
         ok = cuda_ok(cudaMemcpyAsync(f->stage, host, need * sizeof(double), cudaMemcpyHostToDevice, st), "field upload");
         if (ok) {
-            k_repack<<<blocks, threads, 0, st>>>(d, f->stage, rows, (int)W, (int)Pd, (int)W);
+            if (f->packed) k_pack_columns<<<blocks, threads, 0, st>>>(d, f->stage, col, rows, (int)W);
+            else k_repack<<<blocks, threads, 0, st>>>(d, f->stage, rows, (int)W, (int)Pd, (int)W);
             count_launch(1);
             ok = cuda_ok(cudaGetLastError(), "repack");
         }
     } else {
-        k_repack<<<blocks, threads, 0, st>>>(f->stage, d, rows, (int)W, (int)W, (int)Pd);
+        if (f->packed) k_unpack_columns<<<blocks, threads, 0, st>>>(f->stage, d, col, rows, (int)W);
+        else k_repack<<<blocks, threads, 0, st>>>(f->stage, d, rows, (int)W, (int)W, (int)Pd);
         count_launch(1);
         ok = cuda_ok(cudaGetLastError(), "repack") &&
              cuda_ok(cudaMemcpyAsync(host, f->stage, need * sizeof(double), cudaMemcpyDeviceToHost, st), "field download");
@@ -283,9 +328,13 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     const Plan *p = f->plan;
     const int st = *stage;
     const Arrays A = arrays_of(f, st >= ST_PHASE_A ? 1 : 0, *dt, *flux_eps, *bignumber);
+    if (f->packed && !(st >= ST_PHASE_A_WARP && st <= 23)) {
+        std::fprintf(stderr, "fesom2-accelerate: packed fields run the warp-item kernels only (stages 18-23)\n");
+        return;
+    }
     if (st >= ST_PHASE_A_WARP && st <= 23) {
         // 18/19: all owned nodes; 20/21: phase A on the boundary / interior tiles; 22/23: phase B
-        if (!p->wtiles_ok) {
+        if (f->packed ? !p->wtiles_pk_ok : !p->wtiles_ok) {
             std::fprintf(stderr, "fesom2-accelerate: this plan has no warp-item tiles\n");
             return;
         }
@@ -340,6 +389,10 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
     if (h && !halo_valid(h)) return;
     const Arrays A = arrays_of(f, *mode, *dt, *flux_eps, *bignumber);
     const int N = p->N;
+    if (f->packed && *mode != 1) {
+        std::fprintf(stderr, "fesom2-accelerate: packed fields run mode 1 (the warp-item kernels) only\n");
+        return;
+    }
     if (*mode == 0) {
         if (!f->buf[FCT_UV_RHS]) {
             std::fprintf(stderr, "fesom2-accelerate: staged mode needs fields created with UV_rhs\n");
@@ -360,7 +413,7 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
         }
         return;
     }
-    const bool warped = p->wtiles_ok && *mode == 1;
+    const bool warped = (f->packed ? p->wtiles_pk_ok : p->wtiles_ok) && *mode == 1;
     const bool tiled = p->tiles_ok && (*mode == 3 || (*mode == 1 && !warped));
     // one fused phase over a node set: 0 all owned, 1 boundary, 2 interior
     auto phase = [&](int stage, int which) -> bool {

@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -24,6 +25,9 @@ struct Halo {
     std::vector<int> peers, send_off, send_cnt, recv_first, recv_cnt;
     int total_send = 0;
     int *d_send_nodes = nullptr;
+    // packed level storage: first slot of every send column in the send buffer, [total_send + 1]
+    std::vector<unsigned> send_col;
+    unsigned *d_send_col = nullptr;
     double *sendbuf = nullptr;
     size_t sendbuf_doubles = 0;
     cudaStream_t comm_stream = nullptr;
@@ -113,12 +117,71 @@ __global__ void k_halo_pack(const double *__restrict__ plus, const double *__res
     *reinterpret_cast<double2 *>(sendbuf + ((size_t)(t * 2 + 1) * total + i) * P + z) = m;
 }
 
+// packed level storage: one block per send column
+__global__ void k_halo_pack_columns(const double *__restrict__ plus, const double *__restrict__ minus,
+                                    const int *__restrict__ send_nodes, const unsigned *__restrict__ send_col,
+                                    const unsigned *__restrict__ ncol, size_t total_doubles, size_t ts_node,
+                                    double *__restrict__ sendbuf)
+{
+    const int i = blockIdx.x, t = blockIdx.y;
+    const int n = __ldg(send_nodes + i);
+    const unsigned c0 = __ldg(ncol + n), cap = __ldg(ncol + n + 1) - c0, d0 = __ldg(send_col + i);
+    for (unsigned c = threadIdx.x; c < cap; c += blockDim.x) {
+        sendbuf[(size_t)(t * 2 + 0) * total_doubles + d0 + c] = plus[t * ts_node + c0 + c];
+        sendbuf[(size_t)(t * 2 + 1) * total_doubles + d0 + c] = minus[t * ts_node + c0 + c];
+    }
+}
+
+static bool halo_exchange_packed(Fields *f, Halo *h, cudaStream_t s)
+{
+    const Plan *p = f->plan;
+    const int T = f->T;
+    if (h->send_col.empty() || !h->d_send_col) {
+        std::fprintf(stderr, "fesom2-accelerate: this halo was created without the packed column table\n");
+        return false;
+    }
+    const size_t total = h->send_col.back();
+    const size_t need = (size_t)2 * T * total;
+    if (need > h->sendbuf_doubles) {
+        if (h->sendbuf) cudaFree(h->sendbuf);
+        h->sendbuf = nullptr;
+        h->sendbuf_doubles = 0;
+        if (!cuda_ok(cudaMalloc(&h->sendbuf, std::max<size_t>(need, 1) * sizeof(double)), "cudaMalloc(halo)")) return false;
+        h->sendbuf_doubles = need;
+    }
+    double *plus = f->buf[FCT_PLUS], *minus = f->buf[FCT_MINUS];
+    if (h->total_send > 0) {
+        dim3 grid(h->total_send, T);
+        k_halo_pack_columns<<<grid, 64, 0, s>>>(plus, minus, h->d_send_nodes, h->d_send_col, p->d_ncol, total, f->ts_node, h->sendbuf);
+        count_launch(1);
+        if (!cuda_ok(cudaGetLastError(), "halo pack")) return false;
+    }
+    if (!nccl_ok(ncclGroupStart(), "ncclGroupStart")) return false;
+    bool ok = true;
+    for (size_t k = 0; k < h->peers.size() && ok; ++k) {
+        const int peer = h->peers[k];
+        const size_t s0 = h->send_col[h->send_off[k]], sn = h->send_col[h->send_off[k] + h->send_cnt[k]] - s0;
+        const size_t r0 = p->ncol[h->recv_first[k]], rn = p->ncol[h->recv_first[k] + h->recv_cnt[k]] - r0;
+        for (int t = 0; t < T && ok; ++t) {
+            for (int a = 0; a < 2 && ok; ++a) {
+                if (sn > 0)
+                    ok = nccl_ok(ncclSend(h->sendbuf + (size_t)(t * 2 + a) * total + s0, sn, ncclDouble, peer, h->comm, s), "ncclSend");
+                if (ok && rn > 0)
+                    ok = nccl_ok(ncclRecv((a ? minus : plus) + t * f->ts_node + r0, rn, ncclDouble, peer, h->comm, s), "ncclRecv");
+            }
+        }
+    }
+    ok = nccl_ok(ncclGroupEnd(), "ncclGroupEnd") && ok;
+    return ok;
+}
+
 bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
 {
     if (!halo_valid(h) || h->plan != f->plan) {
         std::fprintf(stderr, "fesom2-accelerate: halo does not belong to these fields\n");
         return false;
     }
+    if (f->packed) return halo_exchange_packed(f, h, s);
     const int P = f->P, T = f->T;
     const size_t need = (size_t)2 * T * h->total_send * P;
     if (need > h->sendbuf_doubles) {
@@ -198,6 +261,20 @@ void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int 
     bool ok = cuda_ok(cudaMalloc(&h->d_send_nodes, (size_t)(off > 0 ? off : 1) * sizeof(int)), "cudaMalloc(halo)");
     if (ok && off > 0)
         ok = cuda_ok(cudaMemcpy(h->d_send_nodes, send_nodes, (size_t)off * sizeof(int), cudaMemcpyHostToDevice), "H2D(halo)");
+    if (ok && !p->ncol.empty()) {
+        h->send_col.assign((size_t)off + 1, 0u);
+        for (int i = 0; i < off && ok; ++i) {
+            const int n = send_nodes[i];
+            if (n < 0 || n >= p->N) {
+                std::fprintf(stderr, "fesom2-accelerate: halo send node %d is not an owned node\n", n);
+                ok = false;
+                break;
+            }
+            h->send_col[i + 1] = h->send_col[i] + (p->ncol[n + 1] - p->ncol[n]);
+        }
+        ok = ok && cuda_ok(cudaMalloc(&h->d_send_col, h->send_col.size() * sizeof(unsigned)), "cudaMalloc(halo)") &&
+             cuda_ok(cudaMemcpy(h->d_send_col, h->send_col.data(), h->send_col.size() * sizeof(unsigned), cudaMemcpyHostToDevice), "H2D(halo)");
+    }
     ok = ok && cuda_ok(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking), "stream");
     ok = ok && cuda_ok(cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming), "event");
     ok = ok && cuda_ok(cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming), "event");
@@ -223,6 +300,7 @@ void fct_ale_halo_destroy_(void **halo, int *istat)
     if (!halo_valid(h)) return;
     if (h->comm) ncclCommDestroy(h->comm);
     if (h->d_send_nodes) cudaFree(h->d_send_nodes);
+    if (h->d_send_col) cudaFree(h->d_send_col);
     if (h->sendbuf) cudaFree(h->sendbuf);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     for (auto &e : h->ev)

@@ -36,7 +36,8 @@ struct Fields {
     unsigned magic = FIELDS_MAGIC;
     Plan *plan = nullptr;
     int T = 0;         // tracers
-    int P = 0;         // row pitch (doubles)
+    int P = 0;         // row pitch (doubles); 0: packed level storage (columns back to back)
+    bool packed = false;
     size_t rows = 0;   // N + H
     double *buf[FCT_FIELD_COUNT_INTERNAL] = {nullptr};
     size_t ts_node = 0, ts_edge = 0, ts_uv = 0;

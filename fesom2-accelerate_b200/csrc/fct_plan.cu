@@ -234,40 +234,66 @@ static void schedule_node(std::vector<unsigned short> *v, size_t &len, int ln, i
     }
 }
 
-bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P,
-                     const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out)
+// Column offsets (in doubles) of the packed level storage: node n owns [ncol[n], ncol[n+1]), an even
+// number of slots that holds its nlev-1 active levels plus the bottom interface (fct_adf_v, area);
+// edge g owns [ecol[g], ecol[g+1]), its active levels rounded up to even.
+void packed_columns(const DerivedHost &d, const int *nlev_n, int NT, int G, std::vector<unsigned> &ncol,
+                    std::vector<unsigned> &ecol)
+{
+    ncol.assign((size_t)NT + 1, 0u);
+    for (int n = 0; n < NT; ++n) ncol[n + 1] = ncol[n] + (unsigned)((std::max(nlev_n[n] - 1, 0) + 2) & ~1);
+    std::vector<int> depth((size_t)std::max(G, 1), 0);
+    for (size_t k = 0; k < d.edg.size(); ++k) depth[d.edg[k].x] = FCT_META_DEPTH(d.edg[k].z);
+    ecol.assign((size_t)G + 1, 0u);
+    for (int g = 0; g < G; ++g) ecol[g + 1] = ecol[g] + (unsigned)((depth[g] + 1) & ~1);
+}
+
+bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P, const unsigned *ncol,
+                     const unsigned *ecol, const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out)
 {
     const int count = list ? (int)list->size() : N;
     const int W = 32;
+    const bool packed = ncol && ecol;
     out = WarpTilesHost();
     out.blob_off.assign(1, 0u);
     if (P > 256 || (P & 1) || TN < 1 || TN > 255) return false;
-    if ((long long)NT * P >= (1LL << 32) || (long long)G * P >= (1LL << 32)) return false;
+    if (!packed && ((long long)NT * P >= (1LL << 32) || (long long)G * P >= (1LL << 32))) return false;
     if (d.nbr_off.size() != (size_t)N + 1) return false;
     const int slack = P * 8 + 32;   // masked lanes read up to one row past the last staged byte
+    // global element offset / staged bytes of a node column and of an edge row.  Padded layout: the
+    // active levels (even count); packed layout: the whole column slot, so that consecutive columns
+    // are contiguous in global AND shared memory and their copies merge into one.
+    auto ngoff = [&](int m) { return packed ? ncol[m] : (unsigned)((long long)m * P); };
+    auto egoff = [&](int g) { return packed ? ecol[g] : (unsigned)((long long)g * P); };
+    auto nbytes = [&](int m) { return packed ? (int)(ncol[m + 1] - ncol[m]) * 8 : row_bytes(nlev_n[m] - 1); };
+    auto ebytes = [&](int g, int dg) { return packed ? (int)(ecol[g + 1] - ecol[g]) * 8 : row_bytes(dg); };
+
     std::vector<int> nstamp((size_t)NT, -1), nsoff((size_t)NT, 0), estamp((size_t)std::max(G, 1), -1), esoff((size_t)std::max(G, 1), 0);
-    std::vector<StagedRow> rows, erows;
-    std::vector<unsigned> gaps;   // (first double of the edge region | doubles << 16) to zero in phase A
+    std::vector<int> tile_nodes, halo_nodes, tile_edges, edge_depth((size_t)std::max(G, 1), 0), fresh_n, fresh_e;
     std::vector<int4> hdr, ent;
     std::vector<unsigned short> sched;
     std::vector<std::pair<int, int>> a, b;
     std::vector<char> checked((size_t)N, 0);
+    struct Copy {
+        unsigned goff;
+        int soff, bytes, arr;
+    };
+    std::vector<Copy> copies;
 
     auto need_bytes = [&](size_t nrows, size_t nerows, size_t nn, size_t nent, size_t nsched, int rb, int eb) {
-        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + pad16((int)nerows * 4) + nn * 16 + nent * 16 +
+        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + nn * 16 + nent * 16 +
                             pad16((int)((nsched + W - 1) / W * W) * 2);
         return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack;
     };
 
     int pos = 0, tile = 0;
     while (pos < count) {
-        rows.clear();
-        erows.clear();
-        gaps.clear();
-        hdr.clear();
-        ent.clear();
-        sched.clear();
+        // ---- 1. pick the nodes of the tile: as many as fit the stage ----
+        tile_nodes.clear();
+        halo_nodes.clear();
+        tile_edges.clear();
         int rb = 0, eb = 0, nn = 0;
+        size_t nent = 0, nsched = 0;
         while (pos < count && nn < TN) {
             const int n = list ? (*list)[pos] : pos;
             if (n < 0 || n >= N) return false;
@@ -298,95 +324,141 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
                 if ((d.nbr[nb0].y) > nz) return false;
                 checked[n] = 1;
             }
-            // ---- footprint if this node joins the tile ----
+            // stamp what this node adds; undone if the node does not fit any more
+            fresh_n.clear();
+            fresh_e.clear();
             int add_rb = 0, add_eb = 0;
-            size_t add_rows = 0, add_erows = 0;
-            if (nstamp[n] != tile) {
-                add_rb += row_bytes(nz);
-                ++add_rows;
-            }
-            for (int k = e0; k < e1; ++k) {
-                const int m = d.edg[k].y, g = d.edg[k].x;
+            auto see_node = [&](int m) {
                 if (nstamp[m] != tile) {
-                    add_rb += row_bytes(nlev_n[m] - 1);
-                    ++add_rows;
+                    nstamp[m] = tile;
+                    fresh_n.push_back(m);
+                    add_rb += nbytes(m);
                 }
+            };
+            see_node(n);
+            for (int k = e0; k < e1; ++k) {
+                see_node(d.edg[k].y);
+                const int g = d.edg[k].x;
                 if (estamp[g] != tile) {
-                    add_eb += row_bytes(std::max(nz, nlev_n[m] - 1));
-                    ++add_erows;
+                    estamp[g] = tile;
+                    fresh_e.push_back(g);
+                    edge_depth[g] = FCT_META_DEPTH(d.edg[k].z);
+                    add_eb += ebytes(g, edge_depth[g]);
                 }
             }
             const int s = (nz + 1) / 2;
-            size_t nsched = sched.size();
-            schedule_node(nullptr, nsched, nn, s);
-            const size_t need = need_bytes(rows.size() + add_rows, erows.size() + add_erows, nn + 1, ent.size() + cnt,
-                                           nsched, rb + add_rb, eb + add_eb);
-            if ((int)need > smem_cap || ent.size() + cnt > 65535) {
+            size_t ns = nsched;
+            schedule_node(nullptr, ns, nn, s);
+            const size_t nrows = tile_nodes.size() + halo_nodes.size() + fresh_n.size();
+            const size_t need = need_bytes(nrows, tile_edges.size() + fresh_e.size(), nn + 1, nent + cnt, ns, rb + add_rb, eb + add_eb);
+            if ((int)need > smem_cap || nent + cnt > 65535) {
+                for (int m : fresh_n) nstamp[m] = -1;
+                for (int g : fresh_e) estamp[g] = -1;
                 if (nn == 0) return false;
                 break;
             }
-            // ---- commit ----
-            auto touch = [&](int m) {
-                if (nstamp[m] != tile) {
-                    nstamp[m] = tile;
-                    nsoff[m] = rb;
-                    const int bytes = row_bytes(nlev_n[m] - 1);
-                    rows.push_back({(unsigned)((long long)m * P), rb, bytes});
-                    rb += bytes;
-                }
-                return nsoff[m];
-            };
-            const int own = touch(n);
-            hdr.push_back(make_int4((int)((long long)n * P), nz | (std::min(std::max(d.fillmin[n], 0), 255) << 8) | ((d.nbr[d.nbr_off[n]].y & 0xff) << 16),
-                                    own, (int)ent.size() | (cnt << 16)));
-            for (int k = e0; k < e1; ++k) {
-                const int4 e = d.edg[k];
-                const int other = touch(e.y);
-                if (estamp[e.x] != tile) {
-                    // the row's slot reaches down to the deeper of its two end columns; what the copy
-                    // does not deliver (levels below the edge depth, the pad level of an odd depth) is
-                    // zeroed by phase A's converter warp, so b1 horizontal needs no level mask
-                    estamp[e.x] = tile;
-                    esoff[e.x] = eb;
-                    const int dg = FCT_META_DEPTH(e.z);
-                    const int slot = row_bytes(std::max(nz, nlev_n[e.y] - 1));
-                    erows.push_back({(unsigned)((long long)e.x * P), eb, row_bytes(dg)});
-                    if (slot / 8 > dg) gaps.push_back((unsigned)(eb / 8 + dg) | ((unsigned)(slot / 8 - dg) << 16));
-                    eb += slot;
-                }
-                const unsigned meta = (unsigned)FCT_META_DEPTH(e.z) | (FCT_META_WRITER(e.z) ? 0x40000000u : 0u) |
-                                      (FCT_META_SECOND(e.z) ? 0x80000000u : 0u);
-                ent.push_back(make_int4(esoff[e.x], other, (int)meta, (int)((long long)e.x * P)));
-            }
-            {
-                size_t len = sched.size();
-                schedule_node(&sched, len, nn, s);
-            }
-            out.slots += s;
-            out.edge_uses += cnt;
+            for (int m : fresh_n)
+                if (m != n) halo_nodes.push_back(m);
+            for (int g : fresh_e) tile_edges.push_back(g);
+            tile_nodes.push_back(n);
+            rb += add_rb;
+            eb += add_eb;
+            nent += cnt;
+            nsched = ns;
             ++nn;
             ++pos;
         }
+        // a node first seen as a neighbour may have joined the tile later: it is an own row
+        {
+            std::vector<int> keep;
+            for (int m : halo_nodes) {
+                bool own = false;
+                if (m < N)
+                    for (int t : tile_nodes)
+                        if (t == m) {
+                            own = true;
+                            break;
+                        }
+                if (!own) keep.push_back(m);
+            }
+            halo_nodes.swap(keep);
+        }
+        // ---- 2. lay the stage out: own columns first, in node order, then the halo columns; edge
+        //      rows in ascending edge id.  Runs that are contiguous in global memory are then also
+        //      contiguous in shared memory and travel as one bulk copy. ----
+        copies.clear();
+        auto add_copy = [&](unsigned goff, int soff, int bytes, int arr) {
+            if (bytes <= 0) return;
+            if (!copies.empty()) {
+                Copy &c = copies.back();
+                if (c.arr == arr && c.goff + (unsigned)(c.bytes / 8) == goff && c.soff + c.bytes == soff && c.bytes + bytes <= (1 << 17)) {
+                    c.bytes += bytes;
+                    return;
+                }
+            }
+            copies.push_back({goff, soff, bytes, arr});
+        };
+        int off = 0;
+        std::sort(halo_nodes.begin(), halo_nodes.end());
+        for (int pass = 0; pass < 2; ++pass)
+            for (int m : (pass == 0 ? tile_nodes : halo_nodes)) {
+                nsoff[m] = off;
+                off += nbytes(m);
+            }
+        if (off != rb) return false;
+        for (int arr = 0; arr < 2; ++arr)
+            for (int pass = 0; pass < 2; ++pass)
+                for (int m : (pass == 0 ? tile_nodes : halo_nodes)) add_copy(ngoff(m), nsoff[m] + arr * rb, nbytes(m), arr);
+        std::sort(tile_edges.begin(), tile_edges.end());
+        off = 0;
+        for (int g : tile_edges) {
+            esoff[g] = off;
+            off += ebytes(g, edge_depth[g]);
+        }
+        if (off != eb) return false;
+        for (int g : tile_edges) add_copy(egoff(g), esoff[g] + 2 * rb, ebytes(g, edge_depth[g]), 2);
+        // ---- 3. node headers, edge entries, schedule ----
+        hdr.clear();
+        ent.clear();
+        sched.clear();
+        for (int i = 0; i < nn; ++i) {
+            const int n = tile_nodes[i];
+            const int nz = std::max(nlev_n[n] - 1, 0);
+            const int e0 = d.edg_off[n], e1 = d.edg_off[n + 1];
+            hdr.push_back(make_int4((int)ngoff(n), nz | (std::min(std::max(d.fillmin[n], 0), 255) << 8) | ((d.nbr[d.nbr_off[n]].y & 0xff) << 16),
+                                    nsoff[n], (int)ent.size() | ((e1 - e0) << 16)));
+            for (int k = e0; k < e1; ++k) {
+                const int4 e = d.edg[k];
+                const unsigned meta = (unsigned)FCT_META_DEPTH(e.z) | (FCT_META_WRITER(e.z) ? 0x40000000u : 0u) |
+                                      (FCT_META_SECOND(e.z) ? 0x80000000u : 0u);
+                ent.push_back(make_int4(esoff[e.x], nsoff[e.y], (int)meta, (int)egoff(e.x)));
+            }
+            size_t len = sched.size();
+            schedule_node(&sched, len, i, (nz + 1) / 2);
+            out.slots += (nz + 1) / 2;
+            out.edge_uses += e1 - e0;
+        }
         sched.resize((sched.size() + W - 1) / W * W, (unsigned short)WT_IDLE);
-        // ---- assemble the blob ----
+        // ---- 4. assemble the blob ----
+        // spread the copies over the issuer warps by size: largest first, dealt round-robin by the
+        // strided loop of the kernel
+        std::stable_sort(copies.begin(), copies.end(), [](const Copy &x, const Copy &y) { return x.bytes > y.bytes; });
         const int off_rows = WT_HDR_BYTES;
-        const int n_copies = 2 * (int)rows.size() + (int)erows.size();
-        const int off_gaps = off_rows + pad16(n_copies * 8);
-        const int off_hdr = off_gaps + pad16((int)gaps.size() * 4);
+        const int n_copies = (int)copies.size();
+        const int off_hdr = off_rows + pad16(n_copies * 8);
         const int off_ent = off_hdr + (int)hdr.size() * 16;
         const int off_sched = off_ent + (int)ent.size() * 16;
         const int blob_bytes = off_sched + pad16((int)sched.size() * 2);
         long long tx = 0;
-        for (auto &r : rows) tx += 2LL * r.bytes;
-        for (auto &r : erows) tx += r.bytes;
-        if (tx >= (1 << 20) || 2 * rb + eb >= (1 << 20)) return false;   // mbarrier transaction-count range, 16-bit offsets
+        for (auto &c : copies) tx += c.bytes;
+        if (tx >= (1 << 20) || 2 * rb + eb >= (1 << 18)) return false;   // mbarrier transaction-count range, 14-bit offsets
         std::vector<unsigned char> buf((size_t)blob_bytes, 0);
         int *h = reinterpret_cast<int *>(buf.data());
         h[0] = n_copies;
-        h[1] = (int)erows.size();
+        h[1] = (int)tile_edges.size();
         h[2] = nn;
         h[3] = (int)sched.size() / W;
-        h[4] = (int)rows.size();
+        h[4] = (int)(tile_nodes.size() + halo_nodes.size());
         h[5] = off_hdr;
         h[6] = off_ent;
         h[7] = off_sched;
@@ -394,26 +466,10 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         h[9] = rb;
         h[10] = eb;
         h[11] = (int)tx;
-        h[12] = (int)gaps.size();
-        h[13] = off_gaps;
-        if (!gaps.empty()) std::memcpy(buf.data() + off_gaps, gaps.data(), gaps.size() * 4);
         {
-            // copy list: the rows of the three regions interleaved, so that the issuer warps (which
-            // take consecutive 32-entry chunks) all touch every array; zero-length rows are dropped
             int2 *t = reinterpret_cast<int2 *>(buf.data() + off_rows);
-            int k = 0;
-            auto put = [&](const StagedRow &r, int region_off, int arr) {
-                if (r.bytes > 0) t[k++] = make_int2((int)r.goff, ((r.soff + region_off) >> 4) | ((r.bytes >> 4) << 16) | (arr << 24));
-            };
-            const size_t nmax = std::max(rows.size(), erows.size());
-            for (size_t i = 0; i < nmax; ++i) {
-                if (i < rows.size()) {
-                    put(rows[i], 0, 0);
-                    put(rows[i], rb, 1);
-                }
-                if (i < erows.size()) put(erows[i], 2 * rb, 2);
-            }
-            h[0] = k;
+            for (int k = 0; k < n_copies; ++k)
+                t[k] = make_int2((int)copies[k].goff, (copies[k].soff >> 4) | ((copies[k].bytes >> 4) << 14) | (copies[k].arr << 28));
         }
         if (!hdr.empty()) std::memcpy(buf.data() + off_hdr, hdr.data(), hdr.size() * 16);
         if (!ent.empty()) std::memcpy(buf.data() + off_ent, ent.data(), ent.size() * 16);
@@ -424,8 +480,9 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         out.blob_off.push_back((unsigned)out.blob.size());
         out.smem_bytes = std::max(out.smem_bytes, 16 + blob_bytes + 2 * rb + eb + slack);
         out.nodes += nn;
-        out.staged_rows += (long long)rows.size();
-        out.staged_erows += (long long)erows.size();
+        out.staged_rows += (long long)(tile_nodes.size() + halo_nodes.size());
+        out.staged_erows += (long long)tile_edges.size();
+        out.copies += n_copies;
         out.lanes += (long long)sched.size();
         ++tile;
     }
@@ -442,7 +499,7 @@ extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *my
                                       int *nl, int *nlevels_nod2D, int *nlevels_elem2D, int *elem2D_nodes,
                                       int *nod_in_elem2D_num, int *nod_in_elem2D, int *nod_in_elem2D_dim,
                                       int *edges, int *edge_tri, int *tile_nodes, int *smem_cap,
-                                      int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
+                                      int *which, int *packed, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
                                       unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat)
 {
     using namespace fct;
@@ -457,7 +514,11 @@ extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *my
     const std::vector<int> *list = *which == 1 ? &d.boundary : (*which == 2 ? &d.interior : nullptr);
     WarpTilesHost h;
     const int P = (*nl + 7) & ~7;
-    if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, list, *tile_nodes, *smem_cap, h)) {
+    // *packed != 0: the packed level storage (columns hold their slots back to back)
+    std::vector<unsigned> ncol, ecol;
+    if (*packed) packed_columns(d, nlevels_nod2D, N + H, *myDim_edge2D, ncol, ecol);
+    if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, *packed ? ncol.data() : nullptr,
+                         *packed ? ecol.data() : nullptr, list, *tile_nodes, *smem_cap, h)) {
         *istat = 2;   // mesh not eligible
         return;
     }

@@ -48,7 +48,7 @@ struct WarpTilesHost {
     std::vector<unsigned> blob_off;   // 16-byte units
     int ntiles = 0, smem_bytes = 0;
     // statistics (FCT_VERBOSE)
-    long long nodes = 0, staged_rows = 0, staged_erows = 0, edge_uses = 0, slots = 0, lanes = 0;
+    long long nodes = 0, staged_rows = 0, staged_erows = 0, edge_uses = 0, slots = 0, lanes = 0, copies = 0;
 };
 // Greedy tiling of `list` (nullptr: the identity 0..N-1): a tile closes after TN nodes or when its
 // shared-memory footprint (blob + two staged node-row regions + the edge-row region) would exceed
@@ -56,8 +56,12 @@ struct WarpTilesHost {
 // Returns false when the mesh is not a plain triangulation (ring neighbours == edge neighbours
 // with equal depths, every edge at most as deep as both of its end nodes) or an offset does not
 // fit its field: the caller then keeps the other kernels.
-bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P,
-                     const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out);
+// ncol / ecol: column offsets of the packed level storage (packed_columns), or null for the padded
+// layout (row = index * P).
+bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P, const unsigned *ncol,
+                     const unsigned *ecol, const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out);
+void packed_columns(const DerivedHost &d, const int *nlev_n, int NT, int G, std::vector<unsigned> &ncol,
+                    std::vector<unsigned> &ecol);
 
 struct Plan {
     unsigned magic = 0x504c414eu;
@@ -73,6 +77,11 @@ struct Plan {
     // warp-item kernels: one tile set serves both phases; [0 all owned, 1 boundary, 2 interior]
     WarpTilesDev wtiles[3] = {};
     bool wtiles_ok = false;
+    // packed level storage (fast path only): columns back to back, active levels only
+    std::vector<unsigned> ncol, ecol;             // host: [N+H+1], [G+1] column offsets in doubles
+    const unsigned *d_ncol = nullptr, *d_ecol = nullptr;
+    WarpTilesDev wtiles_pk[3] = {};
+    bool wtiles_pk_ok = false;
     std::vector<void *> owned;   // device allocations to free
 };
 

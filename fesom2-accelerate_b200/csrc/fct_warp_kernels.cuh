@@ -58,8 +58,6 @@ constexpr int WT_SMEM_MAX = 227 * 1024;
 //  [0] node rows  [1] edge rows  [2] nodes  [3] warp items
 //  [4] byte offset of the edge-row table  [5] of the node headers  [6] of the entries  [7] of the schedule
 //  [8] blob bytes  [9] bytes of ONE staged node-row region  [10] bytes of the edge-row region  [11] bytes the row copies deliver
-//  [12] gaps  [13] byte offset of the gap list: unsigned {first double in the edge region | doubles << 16}, the part of
-//       every edge-row slot no copy fills (phase A zeroes it: b1 horizontal then needs no level mask)
 // schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
 // node-row table at byte 64: int2 {global element offset of the row, (16-byte units) smem offset | size << 16}
 // node header int4: {node*pitch, nz | fillmin << 8 | self depth << 16, smem byte offset of the own row, first entry | entries << 16}
@@ -169,8 +167,7 @@ __device__ __forceinline__ double limit_quotient(double a, double b)
 //   the (idle) FP64 pipe instead of compare + select on the (busy) ALU pipe:
 //     max(0, q) = (q + |q|) / 2 and min(0, q) = (q - |q|) / 2 exactly, q = h * s with s = +-1, so
 //     p = fma(fma(h, s, |h|), 0.5, p) rounds once, to the same value as p + max(0, q); a
-//     non-positive q adds +0, which changes neither p >= +0 nor m <= +0.  No level mask: below the
-//     edge depth the staged row holds zeros (the converter warp fills what no copy delivers).
+//     non-positive q adds +0, which changes neither p >= +0 nor m <= +0.
 __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, const double2 &y, const double2 &h,
                                           double &hi0, double &hi1, double &lw0, double &lw1, double &p0,
                                           double &p1, double &m0, double &m1)
@@ -196,16 +193,16 @@ __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, co
         "selp.f64 %3, %13, %3, q;\n"
         "abs.f64 a, %14;\n"
         "fma.rn.f64 t, %14, s, a;\n"
-        "fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
+        "@P0 fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
         "neg.f64 a, a;\n"
         "fma.rn.f64 t, %14, s, a;\n"
-        "fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
+        "@P0 fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
         "abs.f64 a, %15;\n"
         "fma.rn.f64 t, %15, s, a;\n"
-        "fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
+        "@P1 fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
         "neg.f64 a, a;\n"
         "fma.rn.f64 t, %15, s, a;\n"
-        "fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
+        "@P1 fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
         "}"
         : "+d"(hi0), "+d"(hi1), "+d"(lw0), "+d"(lw1), "+d"(p0), "+d"(p1), "+d"(m0), "+d"(m1)
         : "r"(z0), "r"(meta), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y), "d"(h.x), "d"(h.y));
@@ -311,9 +308,8 @@ struct WtView {
     unsigned char *blob, *rowsA, *rowsB, *erows;
     const int4 *hdr, *ent;
     const unsigned short *sched;
-    int rows_bytes, erows_bytes, tx_bytes, n_gaps;
+    int rows_bytes, erows_bytes, tx_bytes;
     const int2 *copies;
-    const unsigned *gaps;
 };
 
 __device__ __forceinline__ WtView wt_view(unsigned char *stage)
@@ -323,9 +319,6 @@ __device__ __forceinline__ WtView wt_view(unsigned char *stage)
     const int4 h0 = reinterpret_cast<const int4 *>(stage)[0];
     const int4 h1 = reinterpret_cast<const int4 *>(stage)[1];
     const int4 h2 = reinterpret_cast<const int4 *>(stage)[2];
-    const int4 h3 = reinterpret_cast<const int4 *>(stage)[3];
-    v.n_gaps = h3.x;
-    v.gaps = reinterpret_cast<const unsigned *>(stage + h3.y);
     v.n_copies = h0.x;
     v.n_nodes = h0.z;
     v.n_witems = h0.w;
@@ -661,8 +654,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             const uint32_t sa = smem_u32(V.rowsA);
             for (int u = (warp - 1) * 32 + lane; u < V.n_copies; u += NPW * 32) {
                 const int2 r = V.copies[u];
-                const uint32_t so = ((uint32_t)r.y & 0xffffu) << 4, sz = (((uint32_t)r.y >> 16) & 0xffu) << 4;
-                const uint32_t arr = ((uint32_t)r.y >> 24) & 3u;
+                const uint32_t so = ((uint32_t)r.y & 0x3fffu) << 4, sz = (((uint32_t)r.y >> 14) & 0x3fffu) << 4;
+                const uint32_t arr = ((uint32_t)r.y >> 28) & 3u;
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 if (T.diag == 0 || (T.diag == 1 && arr != 2)) bulk_g2s(sa + so, src, sz, b_rows(s));
             }
@@ -677,11 +670,6 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             if (tile_of[s] < 0) break;
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1);
-            for (int i = cl; i < V.n_gaps; i += 32 * WT_CONVERTERS) {
-                const unsigned g = V.gaps[i];
-                double *z = reinterpret_cast<double *>(V.erows) + (g & 0xffffu);
-                for (unsigned c = 0; c < (g >> 16); ++c) z[c] = 0.;
-            }
             double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
             const int n16 = V.rows_bytes >> 4;
 #pragma unroll 4

@@ -216,15 +216,25 @@ class DeviceFields:
                   "fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus")
     STATIC = ("area", "area_inv", "hnode", "hnode_new")
 
-    def __init__(self, plan: DevicePlan, ntracers: int = 1, with_uv: bool = True):
+    def __init__(self, plan: DevicePlan, ntracers: int = 1, with_uv: bool = True, packed: bool = False):
+        """packed: the packed level storage of the fast path (active levels only, mode 1 only)."""
         self.lib = abi.load()
         self.plan = plan
         self.T = ntracers
-        self.with_uv = with_uv
+        self.packed = packed
+        self.with_uv = with_uv and not packed
         self.h = C.c_void_p()
         st = C.c_int()
-        self.lib.fct_ale_fields_create_(C.byref(self.h), C.byref(plan.h), ci(ntracers),
-                                        ci(1 if with_uv else 0), C.byref(st))
+        if packed:
+            self.lib.fct_ale_fields_create_packed_(C.byref(self.h), C.byref(plan.h), ci(ntracers), C.byref(st))
+            m = plan.m
+            z = np.arange(m.nl)[None, :]
+            # levels that own a slot on the device (a download returns zeros elsewhere)
+            self._nslot = z < ((np.maximum(m.nlevels_nod2D.astype(np.int64) - 1, 0) + 2) & ~1)[:, None]
+            self._eslot = z < ((m.edge_depth().astype(np.int64) + 1) & ~1)[:, None]
+        else:
+            self.lib.fct_ale_fields_create_(C.byref(self.h), C.byref(plan.h), ci(ntracers),
+                                            ci(1 if with_uv else 0), C.byref(st))
         if st.value != 0:
             raise abi.AbiError("fct_ale_fields_create_ failed (out of device memory?)")
         self.stream = abi.Stream()
@@ -239,8 +249,17 @@ class DeviceFields:
     def upload_field(self, name: str, host: np.ndarray, tracer: int = 0):
         self._copy(self.lib.fct_ale_field_upload_, name, tracer, host)
 
-    def download_field(self, name: str, host: np.ndarray, tracer: int = 0):
-        self._copy(self.lib.fct_ale_field_download_, name, tracer, host)
+    def download_field(self, name: str, host: np.ndarray, tracer: int = 0, merge: bool = True):
+        """Asynchronous download.  Packed fields: `merge` keeps the host's values in the cells that
+        have no slot on the device (synchronises); without it those cells come back as zeros."""
+        if self.packed and merge:
+            tmp = np.empty_like(host)
+            self._copy(self.lib.fct_ale_field_download_, name, tracer, tmp)
+            self.stream.sync()
+            slot = (self._eslot if name.startswith("fct_adf_h") else self._nslot)[:, :host.shape[1]]
+            np.copyto(host, tmp, where=slot)
+        else:
+            self._copy(self.lib.fct_ale_field_download_, name, tracer, host)
 
     def upload(self, f: Fields, tracer: int = 0, static: bool = True, outputs: bool = True):
         names = ["ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "del_ttf_advvert", "del_ttf_advhoriz"]
@@ -296,7 +315,7 @@ class DeviceFields:
             self.upload_field(k, getattr(f, k), tracer)
         st = self.step(f, mode=mode, halo=halo, sync=False)
         for k in self.STEP_RESULTS:
-            self.download_field(k, getattr(out, k), tracer)
+            self.download_field(k, getattr(out, k), tracer, merge=False)
         self.stream.sync()
         return st
 

@@ -189,14 +189,15 @@ void fct_ale_plan_create_(void **plan, int *myDim_nod2D, int *eDim_nod2D, int *m
                           int *nod_in_elem2D_dim, int *edges, int *edge_tri, int *istat);
 void fct_ale_plan_destroy_(void **plan, int *istat);
 /* Host-only introspection of the inspector (no CUDA device needed): the warp-item tile tables the
- * fused kernels consume for node set *which (0 all owned, 1 boundary, 2 interior), as 32-bit words
+ * fused kernels consume for node set *which (0 all owned, 1 boundary, 2 interior) in the padded
+ * (*packed == 0) or packed (*packed != 0) level storage, as 32-bit words
  * (layout: fesom2-accelerate_b200/csrc/fct_warp_kernels.cuh).  *istat: 0 ok, 1 malformed mesh,
  * 2 mesh not eligible for the warp-item kernels, 3 buffers too small. */
 void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D, int *myDim_edge2D,
                            int *nl, int *nlevels_nod2D, int *nlevels_elem2D, int *elem2D_nodes,
                            int *nod_in_elem2D_num, int *nod_in_elem2D, int *nod_in_elem2D_dim,
                            int *edges, int *edge_tri, int *tile_nodes, int *smem_cap,
-                           int *which, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
+                           int *which, int *packed, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
                            unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat);
 /* which fused kernels *mode 1 of fct_ale_step_ will run on this plan: the persistent TMA-staged
  * warp-item kernels (*warp_tiles), else the tile-staged ones (*staged_tiles), else the untiled */
@@ -208,6 +209,13 @@ void fct_ale_plan_pitch_(void **plan, int *pitch);
 /* Device arrays for a batch of *ntracers tracers on a plan, rows padded to the plan pitch.
  * *with_uv_rhs != 0 also allocates UV_rhs (needed by the staged mode only). */
 void fct_ale_fields_create_(void **fields, void **plan, int *ntracers, int *with_uv_rhs, int *istat);
+/* The same in the PACKED level storage, the layout of the fast path: every column holds only its
+ * active levels (+ the bottom interface), columns back to back, so no DRAM granule is wasted on
+ * the tail of a row, the footprint shrinks by the inactive share (about 30 %), and the own columns
+ * of a tile travel as one bulk copy per array.  Packed fields support fct_ale_step_ mode 1 (plans
+ * of plain triangulations), upload / download and the halo exchange; a download fills the levels
+ * that have no slot with zeros. */
+void fct_ale_fields_create_packed_(void **fields, void **plan, int *ntracers, int *istat);
 void fct_ale_fields_destroy_(void **fields, int *istat);
 
 /* Field identifiers for upload / download */

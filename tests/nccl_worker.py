@@ -1,6 +1,7 @@
 """Worker of tests/test_gpu_multi.py: one rank per GPU, partition r of a mesh on GPU r, the fused
 step with the NVLink halo exchange (NCCL) inside, owned results checked against the single-domain
-oracle bit for bit.  Modes: 1 = tile-staged overlapped schedule, 2 = untiled, 0 = staged."""
+oracle bit for bit.  Modes: 1 = persistent warp-item kernels, overlapped schedule (also in the packed
+level storage), 3 = tile-staged, 2 = untiled, 0 = staged."""
 import importlib
 import os
 import sys
@@ -42,8 +43,8 @@ def main():
     halo = harness.HaloLink(plan, part, uid)
     n = part.mesh.myDim_nod2D
     g = part.mesh.node_gid[:n]
-    for mode in (1, 2, 0):
-        df = harness.DeviceFields(plan, T, with_uv=True)
+    for mode, packed in ((1, True), (1, False), (3, False), (2, False), (0, False)):
+        df = harness.DeviceFields(plan, T, with_uv=True, packed=packed)
         lfs = [mesh_mod.slice_fields(f, part) for f in fs]
         for t in range(T):
             df.upload(lfs[t], tracer=t, static=(t == 0))

@@ -107,6 +107,44 @@ def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, kno
             abi.tune(k, v)
 
 
+@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "deep"])
+def test_packed_level_storage(mesh_mod, harness, oracle_mod, name):
+    """The fast path's own layout: columns hold their active levels only, back to back."""
+    m, f = cases(mesh_mod, name)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, packed=True)
+    df.upload(f)
+    assert df.step(f, mode=1) == 10
+    check(df.download(f, mode=1), want)
+    with pytest.raises(Exception):
+        df.stage("a1", f)                    # stage kernels need the padded layout: refused, not emulated
+    assert df.step(f, mode=0) == 0
+    df.free()
+    plan.free()
+
+
+def test_packed_multi_tracer(mesh_mod, harness, oracle_mod):
+    m = mesh_mod.make_workload("pi")
+    T = 3
+    fs = [mesh_mod.make_fields(m, seed=1 + t) for t in range(T)]
+    for t in range(1, T):
+        for k in ("area", "area_inv", "hnode", "hnode_new"):
+            setattr(fs[t], k, fs[0].__dict__[k])
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, T, packed=True)
+    for t in range(T):
+        df.upload(fs[t], tracer=t, static=(t == 0))
+    assert df.step(fs[0], mode=1) == 10
+    for t in range(T):
+        want = fs[t].copy()
+        oracle_mod.fct_ale(m, want)
+        check(df.download(fs[t], tracer=t, mode=1), want)
+    df.free()
+    plan.free()
+
+
 def test_stage_by_stage(mesh_mod, harness, oracle_mod):
     """Each stage kernel against the oracle stage it replaces (the reference's NUM_KERNELS staged
     execution, src/fesom2-accelerate.cu:256-335)."""
@@ -207,7 +245,7 @@ def test_step_is_repeatable_and_deterministic(mesh_mod, harness):
 
 
 @pytest.mark.parametrize("nparts", [2, 5])
-@pytest.mark.parametrize("tiled", [False, True, "warp"])
+@pytest.mark.parametrize("tiled", [False, True, "warp", "packed"])
 def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled):
     """Every partition of a mesh run on this GPU with the halo exchange emulated through the host:
     owned results of all partitions must reproduce the single-domain oracle bit for bit (boundary /
@@ -218,10 +256,10 @@ def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled):
     parts = mesh_mod.partition_mesh(m, nparts)
     plans = [harness.DevicePlan(p.mesh) for p in parts]
     lfs = [mesh_mod.slice_fields(f, p) for p in parts]
-    dfs = [harness.DeviceFields(pl, 1, with_uv=False) for pl in plans]
+    dfs = [harness.DeviceFields(pl, 1, with_uv=False, packed=(tiled == "packed")) for pl in plans]
     stA = ["phaseA_tile_boundary", "phaseA_tile_interior"] if tiled else ["phaseA"]
     stB = ["phaseB_tile_interior", "phaseB_tile_boundary"] if tiled else ["phaseB"]
-    if tiled == "warp":
+    if tiled in ("warp", "packed"):
         stA = ["phaseA_warp_boundary", "phaseA_warp_interior"]
         stB = ["phaseB_warp_interior", "phaseB_warp_boundary"]
     for df, lf in zip(dfs, lfs):

@@ -15,7 +15,7 @@ from conftest import bits_equal
 INF = float("inf")
 
 
-def inspect(abi, m, tile_nodes=64, smem_cap=74 * 1024, which=0):
+def inspect(abi, m, tile_nodes=64, smem_cap=74 * 1024, which=0, packed=0):
     lib = abi.load()
     cap_words = 64 * 1024 * 1024 // 4
     blob = np.zeros(cap_words, np.uint32)
@@ -27,7 +27,7 @@ def inspect(abi, m, tile_nodes=64, smem_cap=74 * 1024, which=0):
         abi.ci(m.nl), abi.iptr(m.nlevels_nod2D), abi.iptr(m.nlevels_elem),
         abi.iptr(m.elem2D_nodes.reshape(-1)), abi.iptr(m.nod_in_elem2D_num),
         abi.iptr(m.nod_in_elem2D.reshape(-1)), abi.ci(m.nod_in_elem2D_dim), abi.iptr(m.edges.reshape(-1)),
-        abi.iptr(m.edge_tri.reshape(-1)), abi.ci(tile_nodes), abi.ci(smem_cap), abi.ci(which),
+        abi.iptr(m.edge_tri.reshape(-1)), abi.ci(tile_nodes), abi.ci(smem_cap), abi.ci(which), abi.ci(packed),
         C.byref(C.c_longlong(cap_words * 4)), blob.ctypes.data_as(u32p), abi.ci(off.size),
         off.ctypes.data_as(u32p), C.byref(nt), C.byref(sm), C.byref(st))
     return st.value, nt.value, sm.value, blob, off
@@ -41,8 +41,6 @@ class Tile:
         h = np.frombuffer(b, np.int32, 16)
         (self.n_copies, self.n_erows, self.n_nodes, self.n_witems, self.n_rows, off_hdr, off_ent, off_sched,
          blob_bytes, self.rows_bytes, self.erows_bytes, self.tx) = [int(x) for x in h[:12]]
-        n_gaps, off_gaps = int(h[12]), int(h[13])
-        self.gaps = np.frombuffer(b, np.uint32, n_gaps, off_gaps)
         assert blob_bytes == len(b)
         self.copies = np.frombuffer(b, np.uint32, 2 * self.n_copies, 64).reshape(-1, 2)
         self.hdr = np.frombuffer(b, np.uint32, 4 * self.n_nodes, off_hdr).reshape(-1, 4)
@@ -61,7 +59,7 @@ class Tile:
         tx = 0
         for goff, pk in self.copies:
             pk = int(pk)
-            so, sz, arr = (pk & 0xffff) * 2, ((pk >> 16) & 0xff) * 2, (pk >> 24) & 3     # in doubles
+            so, sz, arr = (pk & 0x3fff) * 2, ((pk >> 14) & 0x3fff) * 2, (pk >> 28) & 3     # in doubles
             assert sz > 0 and arr < 3 and so + sz <= lim[arr] and so >= (0, ra, 2 * ra)[arr]
             assert np.isnan(img[so:so + sz]).all(), "two copies overlap"
             img[so:so + sz] = src[arr][goff:goff + sz]
@@ -84,13 +82,43 @@ def pad(a, P):
     return out.reshape(-1)
 
 
-def emulate(m, f, blob, off, ntiles):
-    """Both fused phases on the padded layout; returns the dict of padded result arrays."""
+class Packed:
+    """The packed level storage: node n owns round_up_even(nlev-1 + 1) slots, edge g round_up_even(depth)."""
+
+    def __init__(self, m):
+        nz = np.maximum(m.nlevels_nod2D.astype(np.int64) - 1, 0)
+        self.ncap = (nz + 2) & ~1
+        self.ecap = (m.edge_depth().astype(np.int64) + 1) & ~1
+        self.ncol = np.concatenate([[0], np.cumsum(self.ncap)])
+        self.ecol = np.concatenate([[0], np.cumsum(self.ecap)])
+
+    def pack(self, a, edge=False):
+        cap, col = (self.ecap, self.ecol) if edge else (self.ncap, self.ncol)
+        out = np.full(int(col[-1]), np.nan)
+        for r in range(a.shape[0]):
+            w = min(int(cap[r]), a.shape[1])
+            out[col[r]:col[r] + w] = a[r, :w]
+        return out
+
+    def unpack(self, v, like, edge=False):
+        cap, col = (self.ecap, self.ecol) if edge else (self.ncap, self.ncol)
+        out = np.array(like)
+        for r in range(like.shape[0]):
+            w = min(int(cap[r]), like.shape[1])
+            out[r, :w] = v[col[r]:col[r] + w]
+        return out
+
+
+def emulate(m, f, blob, off, ntiles, packed=None):
+    """Both fused phases on the padded (or packed) layout; returns the dict of device-layout result arrays."""
     P = (m.nl + 7) & ~7
     L = m.L
-    g = {k: pad(getattr(f, k), P) for k in ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area", "area_inv", "hnode",
-                                            "hnode_new", "del_ttf_advvert", "del_ttf_advhoriz", "fct_ttf_max",
-                                            "fct_ttf_min", "fct_plus", "fct_minus")}
+    names = ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area", "area_inv", "hnode", "hnode_new", "del_ttf_advvert",
+             "del_ttf_advhoriz", "fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus")
+    if packed is None:
+        g = {k: pad(getattr(f, k), P) for k in names}
+    else:
+        g = {k: packed.pack(getattr(f, k), edge=(k == "fct_adf_h")) for k in names}
     g["adf_v_out"] = g["fct_adf_v"].copy()
     g["adf_h_out"] = g["fct_adf_h"].copy()
     dt, eps, big = f.dt, f.flux_eps, f.bignumber
@@ -101,10 +129,6 @@ def emulate(m, f, blob, off, ntiles):
             T = Tile(blob[off[t] * 4: off[t + 1] * 4], P)
             if phase == "A":
                 RA, RB, RE = T.stage(g["fct_LO"], g["ttf"], g["fct_adf_h"])
-                for gp in T.gaps:                                  # the converter warp's zero fill
-                    st, cnt = int(gp) & 0xffff, int(gp) >> 16
-                    assert cnt > 0 and st + cnt <= T.erows_bytes // 8
-                    RE[st:st + cnt] = 0.0
                 lo_, tt_ = RA.copy(), RB.copy()
                 with np.errstate(invalid="ignore"):
                     RA = np.where(lo_ < tt_, tt_, lo_)           # pick_max(lo, ttf)
@@ -170,17 +194,14 @@ def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
             ex, ey, ez, ew = [int(x) for x in T.ent[s["e0"] + k]]
             dg, second = ez & 0xffff, bool(ez >> 31)
             for v in range(2):
-                h = RE[ex // 8 + z0 + v]                          # b1 horizontal is NOT masked in the kernel
-                assert not np.isnan(h), "read of an edge-row byte that was neither staged nor zeroed"
-                assert z0 + v < dg or h == 0.0
-                q = -h if second else h
-                p[v] += pmax(0., q)
-                mm[v] += pmin(0., q)
                 if z0 + v < dg:
-                    x, y = RA[ey // 8 + z0 + v], RB[ey // 8 + z0 + v]
-                    assert not (np.isnan(x) or np.isnan(y)), "read of a byte that was never staged"
+                    x, y, h = RA[ey // 8 + z0 + v], RB[ey // 8 + z0 + v], RE[ex // 8 + z0 + v]
+                    assert not (np.isnan(x) or np.isnan(y) or np.isnan(h)), "read of a byte that was never staged"
                     hi[v] = pmax(hi[v], x)
                     lw[v] = pmin(lw[v], y)
+                    q = -h if second else h
+                    p[v] += pmax(0., q)
+                    mm[v] += pmin(0., q)
         s.update(hi=hi, lw=lw, p=p, m=mm)
         tv.append(s)
     for vl, s in enumerate(tv):
@@ -267,6 +288,20 @@ def unpad(a, P, width):
     return a.reshape(-1, P)[:, :width]
 
 
+def compare_packed(m, f, g, pk, want):
+    """Active cells from the packed arrays, everything else as the inputs had it (what the harness does)."""
+    for k, wk in (("fct_ttf_max", "fct_ttf_max"), ("fct_ttf_min", "fct_ttf_min"), ("fct_plus", "fct_plus"),
+                  ("fct_minus", "fct_minus"), ("adf_v_out", "fct_adf_v"), ("del_ttf_advvert", "del_ttf_advvert"),
+                  ("del_ttf_advhoriz", "del_ttf_advhoriz"), ("adf_h_out", "fct_adf_h")):
+        edge = wk == "fct_adf_h"
+        got = pk.unpack(g[k], getattr(f, wk), edge=edge)
+        w = getattr(want, wk)
+        z = np.arange(w.shape[1])[None, :]
+        depth = m.edge_depth() if edge else m.nlevels_nod2D - 1
+        act = z < depth[:, None]
+        assert bits_equal(np.where(act, got, w), w), k
+
+
 def compare(m, f, g, P, want, owned=None):
     L = m.L
     pairs = [("fct_ttf_max", "fct_ttf_max", L), ("fct_ttf_min", "fct_ttf_min", L), ("fct_plus", "fct_plus", L),
@@ -292,6 +327,27 @@ def test_tables_reproduce_the_oracle(mesh_mod, abi, oracle_mod, name, tn, cap):
     assert st == 0 and nt >= 1 and smem <= cap
     g, P = emulate(m, f, blob, off, nt)
     compare(m, f, g, P, want)
+
+
+@pytest.mark.parametrize("name,tn,cap", [("tiny", 64, 74 * 1024), ("pi", 96, 74 * 1024), ("pi", 7, 30 * 1024)])
+def test_packed_level_storage(mesh_mod, abi, oracle_mod, name, tn, cap):
+    """Columns back to back (active levels only): the tile's own columns and its edge rows in ascending
+    id become runs that travel as single bulk copies."""
+    m = mesh_mod.make_workload(name)
+    f = mesh_mod.make_fields(m)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    st, nt, smem, blob, off = inspect(abi, m, tn, cap, packed=1)
+    assert st == 0 and nt >= 1 and smem <= cap
+    pk = Packed(m)
+    g, P = emulate(m, f, blob, off, nt, packed=pk)
+    compare_packed(m, f, g, pk, want)
+    # far fewer copies than staged rows
+    P = (m.nl + 7) & ~7
+    ncopies = sum(Tile(blob[off[t] * 4: off[t + 1] * 4], P).n_copies for t in range(nt))
+    nrows = sum(2 * Tile(blob[off[t] * 4: off[t + 1] * 4], P).n_rows + Tile(blob[off[t] * 4: off[t + 1] * 4], P).n_erows
+                for t in range(nt))
+    assert ncopies < 0.6 * nrows
 
 
 def test_deep_columns_are_cut_with_ghost_slots(mesh_mod, abi, oracle_mod):

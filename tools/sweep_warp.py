@@ -23,7 +23,7 @@ for TN, cap, nch, wa, wb, npw in cfgs:
     abi.tune("TILE", 0)
     t0 = time.time()
     plan = harness.DevicePlan(m)
-    df = harness.DeviceFields(plan, 1, with_uv=False)
+    df = harness.DeviceFields(plan, 1, with_uv=False, packed=bool(int(os.environ.get('SWEEP_PACKED', '1'))))
     df.upload(f, outputs=False)
     def timeit(fn):
         for _ in range(3): fn()
