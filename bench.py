@@ -161,7 +161,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
-    print(json.dumps(line), flush=True)
+    _RESULT.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -333,7 +333,7 @@ def run_product(args):
                         "api": "fct_ale_field_upload_ x8 / fct_ale_step_ / fct_ale_field_download_ x2 / await_stream_ on page-locked host arrays",
                         "reference_sequence": refseq},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "setup_s": time.time() - t_setup}
-        print(json.dumps(line), flush=True)
+        _RESULT.append(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -341,6 +341,25 @@ def run_product(args):
 
 
 def main():
+    # native libraries (NCCL's version banner, ...) write to file descriptor 1: route it to stderr
+    # for the duration of the run so that stdout carries exactly the one JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if _RESULT:
+        print(_RESULT[0], flush=True)
+
+
+_RESULT = []
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
