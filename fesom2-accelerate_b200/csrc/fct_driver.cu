@@ -364,8 +364,9 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     }
     // consumer / issuer warps: the closest compiled variant (0: default)
     int nwc = env_int(isA ? "FCT_WT_WARPS_A" : "FCT_WT_WARPS_B", 0), npw = env_int("FCT_WT_ISSUERS", 0);
-    nwc = nwc <= 0 ? (isA ? 17 : 19) : nwc;   // 24 warps in all at 80 registers
-    npw = npw <= 0 ? 4 : npw;
+    // 24 warps in all at 80 registers; the packed layout needs a sixth of the bulk copies: two issuers
+    npw = npw <= 0 ? (packed ? 2 : 4) : npw;
+    nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
     constexpr int NV = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     int vi = -1, best = 1 << 30;
     for (int i = 0; i < NV; ++i) {

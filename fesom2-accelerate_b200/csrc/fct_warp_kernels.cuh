@@ -707,11 +707,12 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             while (wi < V.n_witems) {
                 WtEarly En;
                 if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v, tn);
-                const int wnn = grab(s);
+                int raw = 0;   // lane 0 draws now; the broadcast waits until the item is done
+                if (lane == 0) raw = atomicAdd(next_item + s, 1);
                 if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, E);
                 else wt_item_b(A, V, wi, lane, tn, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E);
                 wi = wn;
-                wn = wnn;
+                wn = __shfl_sync(0xffffffffu, raw, 0);
                 E = En;
             }
             __syncwarp();
