@@ -23,7 +23,7 @@ SYMBOLS = [
     "fct_ale_a4_reference_", "fct_ale_pre_comm_",
     "fct_ale_c_acc_", "transfer_var_back_", "transfer_var_back_async_", "free_var_",
     "free_pinned_doubles_", "free_stream_", "fct_ale_set_fused_", "fct_ale_tune_", "fct_ale_launch_count_",
-    "fct_ale_device_info_", "fct_ale_event_create_", "fct_ale_event_record_",
+    "fct_ale_device_info_", "fct_ale_event_create_", "fct_ale_event_record_", "fct_ale_stream_wait_event_",
     "fct_ale_event_elapsed_ms_", "fct_ale_event_destroy_", "fct_ale_mem_info_",
     "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_", "fct_ale_plan_inspect_", "fct_ale_plan_kernels_",
     "fct_ale_fields_create_", "fct_ale_fields_create_packed_", "fct_ale_fields_destroy_", "fct_ale_field_upload_",
@@ -132,6 +132,13 @@ class Stream:
         load().await_stream_(C.byref(self.h), C.byref(st))
         if st.value != 0:
             raise AbiError("await_stream_ failed (see stderr)")
+
+    def wait(self, event: "Event"):
+        """Work issued to this stream from now on starts after `event` (recorded on another stream)."""
+        st = C.c_int()
+        load().fct_ale_stream_wait_event_(C.byref(self.h), C.byref(event.h), C.byref(st))
+        if st.value != 0:
+            raise AbiError("fct_ale_stream_wait_event_ failed")
 
     def free(self):
         st = C.c_int()

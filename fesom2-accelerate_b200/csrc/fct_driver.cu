@@ -1210,6 +1210,11 @@ void fct_ale_event_record_(void **event, void **stream, int *istat)
     *istat = cuda_ok(cudaEventRecord((cudaEvent_t)*event, S(stream)), "cudaEventRecord") ? 0 : 1;
 }
 
+void fct_ale_stream_wait_event_(void **stream, void **event, int *istat)
+{
+    *istat = cuda_ok(cudaStreamWaitEvent(S(stream), (cudaEvent_t)*event, 0), "cudaStreamWaitEvent") ? 0 : 1;
+}
+
 void fct_ale_event_elapsed_ms_(void **start, void **stop, real_type *ms, int *istat)
 {
     float t = 0.f;

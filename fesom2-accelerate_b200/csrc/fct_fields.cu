@@ -235,7 +235,8 @@ void fct_ale_fields_destroy_(void **fields, int *istat)
     if (!f) return;
     for (double *b : f->buf)
         if (b) cudaFree(b);
-    if (f->stage) cudaFree(f->stage);
+    for (double *b : f->stage)
+        if (b) cudaFree(b);
     f->magic = 0;
     delete f;
     *fields = nullptr;
@@ -266,45 +267,38 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
         *istat = cuda_ok(e, up ? "field upload" : "field download") ? 0 : 1;
         return;
     }
-    // one contiguous PCIe copy through a dense staging buffer + a repack kernel (stream ordered, so
-    // the single buffer serves any sequence of transfers on one stream; callers that spread
-    // transfers of one Fields object over several streams must order them themselves)
+    // one contiguous PCIe copy through a dense staging buffer + a repack kernel.  One buffer per
+    // direction, stream ordered: all uploads of a Fields object belong on one stream, all its
+    // downloads on one (possibly other) stream; ordering between the two is the caller's (events)
     const size_t W = width / sizeof(double), Pd = pitch / sizeof(double), need = rows * W;
-    if (need > f->stage_doubles) {
+    const int dir = up ? 0 : 1;
+    if (need > f->stage_doubles[dir]) {
         cudaStreamSynchronize(st);
-        if (f->stage) cudaFree(f->stage);
-        f->stage = nullptr;
-        f->stage_doubles = 0;
-        size_t want = need;   // size it once for the largest field of this object
-        for (int id = 0; id < FCT_FIELD_COUNT; ++id) {
-            if (!f->buf[id]) continue;
-            const FieldMeta mm = meta_of(id);
-            want = std::max(want, field_rows(f, mm.kind) * (size_t)(f->plan->nl - mm.width_minus) * (id == FCT_UV_RHS ? 2 : 1));
-        }
-        if (!cuda_ok(cudaMalloc(&f->stage, want * sizeof(double)), "cudaMalloc(staging)")) {
-            if (!cuda_ok(cudaMalloc(&f->stage, need * sizeof(double)), "cudaMalloc(staging)")) return;
-            want = need;
-        }
-        f->stage_doubles = want;
+        if (f->stage[dir]) cudaFree(f->stage[dir]);
+        f->stage[dir] = nullptr;
+        f->stage_doubles[dir] = 0;
+        if (!cuda_ok(cudaMalloc(&f->stage[dir], need * sizeof(double)), "cudaMalloc(staging)")) return;
+        f->stage_doubles[dir] = need;
     }
+    double *stage = f->stage[dir];
     const int threads = 256;
     const int blocks = (int)std::min<size_t>((need + threads - 1) / threads, (size_t)148 * 16);
     bool ok;
     const unsigned *col = m.kind == ROW_EDGE ? f->plan->d_ecol : f->plan->d_ncol;
     if (up) {
-        ok = cuda_ok(cudaMemcpyAsync(f->stage, host, need * sizeof(double), cudaMemcpyHostToDevice, st), "field upload");
+        ok = cuda_ok(cudaMemcpyAsync(stage, host, need * sizeof(double), cudaMemcpyHostToDevice, st), "field upload");
         if (ok) {
-            if (f->packed) k_pack_columns<<<blocks, threads, 0, st>>>(d, f->stage, col, rows, (int)W);
-            else k_repack<<<blocks, threads, 0, st>>>(d, f->stage, rows, (int)W, (int)Pd, (int)W);
+            if (f->packed) k_pack_columns<<<blocks, threads, 0, st>>>(d, stage, col, rows, (int)W);
+            else k_repack<<<blocks, threads, 0, st>>>(d, stage, rows, (int)W, (int)Pd, (int)W);
             count_launch(1);
             ok = cuda_ok(cudaGetLastError(), "repack");
         }
     } else {
-        if (f->packed) k_unpack_columns<<<blocks, threads, 0, st>>>(f->stage, d, col, rows, (int)W);
-        else k_repack<<<blocks, threads, 0, st>>>(f->stage, d, rows, (int)W, (int)W, (int)Pd);
+        if (f->packed) k_unpack_columns<<<blocks, threads, 0, st>>>(stage, d, col, rows, (int)W);
+        else k_repack<<<blocks, threads, 0, st>>>(stage, d, rows, (int)W, (int)W, (int)Pd);
         count_launch(1);
         ok = cuda_ok(cudaGetLastError(), "repack") &&
-             cuda_ok(cudaMemcpyAsync(host, f->stage, need * sizeof(double), cudaMemcpyDeviceToHost, st), "field download");
+             cuda_ok(cudaMemcpyAsync(host, stage, need * sizeof(double), cudaMemcpyDeviceToHost, st), "field download");
     }
     *istat = ok ? 0 : 1;
 }

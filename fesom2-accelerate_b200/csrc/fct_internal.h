@@ -41,8 +41,10 @@ struct Fields {
     size_t rows = 0;   // N + H
     double *buf[FCT_FIELD_COUNT_INTERNAL] = {nullptr};
     size_t ts_node = 0, ts_edge = 0, ts_uv = 0;
-    double *stage = nullptr;   // dense staging buffer of field_upload_ / field_download_
-    size_t stage_doubles = 0;
+    // dense staging buffers of field_upload_ / field_download_, one per direction so that an upload
+    // stream and a download stream can run concurrently (PCIe is full duplex)
+    double *stage[2] = {nullptr, nullptr};
+    size_t stage_doubles[2] = {0, 0};
 };
 
 struct Halo;

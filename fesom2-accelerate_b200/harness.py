@@ -319,6 +319,38 @@ class DeviceFields:
         self.stream.sync()
         return st
 
+    def host_steps(self, f: Fields, out: Fields, steps: int, mode: int = 1, halo: Optional[HaloLink] = None,
+                   tracer: int = 0) -> int:
+        """`steps` end-to-end tracer steps back to back for a host-resident caller, with the download
+        of step k (its own stream) overlapping the upload of step k+1: PCIe is full duplex.  Every
+        step uploads all its inputs and downloads its tendencies; del_ttf_adv* (inputs AND results)
+        are uploaded last, after the previous step's download has left the device."""
+        if not hasattr(self, "_dn"):
+            self._dn = abi.Stream()
+            self._ev_step, self._ev_dn = abi.Event(), abi.Event()
+        st = 0
+        first = [k for k in self.STEP_INPUTS if k not in self.STEP_RESULTS]
+        for k in range(steps):
+            for name in first:
+                self.upload_field(name, getattr(f, name), tracer)
+            if k > 0:
+                self.stream.wait(self._ev_dn)
+            for name in self.STEP_RESULTS:
+                self.upload_field(name, getattr(f, name), tracer)
+            st = self.step(f, mode=mode, halo=halo, sync=False)
+            self._ev_step.record(self.stream)
+            self._dn.wait(self._ev_step)
+            for name in self.STEP_RESULTS:
+                stt = C.c_int()
+                self.lib.fct_ale_field_download_(C.byref(self.h), ci(abi.FIELD_IDS[name]), ci(tracer),
+                                                 dptr(getattr(out, name).reshape(-1)), self._dn.ref, C.byref(stt))
+                if stt.value != 0:
+                    raise abi.AbiError(f"download of {name} failed")
+            self._ev_dn.record(self._dn)
+        self._dn.sync()
+        self.stream.sync()
+        return st
+
     def host_step_bytes(self, f: Fields):
         return (sum(getattr(f, k).nbytes for k in self.STEP_INPUTS), sum(getattr(f, k).nbytes for k in self.STEP_RESULTS))
 

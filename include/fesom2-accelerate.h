@@ -172,6 +172,8 @@ void fct_ale_device_info_(char *name64, int *cc_major, int *cc_minor, int *sm_co
 /* CUDA-event timing on the caller's stream (bench.py, the harness): create / record / elapsed */
 void fct_ale_event_create_(void **event, int *istat);
 void fct_ale_event_record_(void **event, void **stream, int *istat);
+/* make *stream wait for *event (ordering between an upload stream and a download stream) */
+void fct_ale_stream_wait_event_(void **stream, void **event, int *istat);
 void fct_ale_event_elapsed_ms_(void **start, void **stop, real_type *ms, int *istat);
 void fct_ale_event_destroy_(void **event, int *istat);
 /* free / total bytes of device memory on the bound device */

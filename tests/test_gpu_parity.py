@@ -145,6 +145,28 @@ def test_packed_multi_tracer(mesh_mod, harness, oracle_mod):
     plan.free()
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_host_resident_steps(mesh_mod, harness, oracle_mod, packed):
+    """The end-to-end path bench.py times: per step upload the inputs, run, download the tendencies, the
+    download of step k on a second stream overlapping the upload of step k+1."""
+    m, f = cases(mesh_mod, "pi")
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=False, packed=packed)
+    df.upload(f)                               # mesh-static fields + defined output cells
+    out = f.copy()
+    assert df.host_steps(f, out, 3, mode=1) == 10
+    act = np.arange(m.L)[None, :] < (m.nlevels_nod2D[:, None] - 1)
+    for k in ("del_ttf_advvert", "del_ttf_advhoriz"):
+        assert bits_equal(getattr(out, k)[act], getattr(want, k)[act]), k
+    assert df.host_step(f, out, mode=1) == 10
+    for k in ("del_ttf_advvert", "del_ttf_advhoriz"):
+        assert bits_equal(getattr(out, k)[act], getattr(want, k)[act]), k
+    df.free()
+    plan.free()
+
+
 def test_stage_by_stage(mesh_mod, harness, oracle_mod):
     """Each stage kernel against the oracle stage it replaces (the reference's NUM_KERNELS staged
     execution, src/fesom2-accelerate.cu:256-335)."""
