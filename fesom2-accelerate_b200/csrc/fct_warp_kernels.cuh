@@ -97,38 +97,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires: a
+// waiting warp issues an instruction every ~20 us instead of spinning, and wakes as soon as the
+// barrier flips
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WT_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 20000;\n"
         "@p bra WT_DONE;\n"
         "bra WT_WAIT;\n"
         "WT_DONE:\n"
         "}" ::"r"(bar), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 
-// producer-side wait: backs off between probes so that an idle producer warp does not compete
-// with the consumers for issue slots
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity)
+// lane 0's draw from a shared-memory counter (the C++ atomicAdd carries warp-aggregation code for
+// a uniform address that a single active lane does not need)
+__device__ __forceinline__ int smem_fetch_add(int *ctr)
 {
-    uint32_t done = 0;
-    for (;;) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(200);
-    }
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(ctr)) : "memory");
+    return old;
 }
 
 __device__ __forceinline__ double flip_sign(double v, unsigned sgn)
@@ -405,8 +398,20 @@ __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, in
 }
 
 // ---- phase A: one warp item ------------------------------------------------------------------------
+// What an item does for its successor right before its edge loop: broadcast the index lane 0 drew
+// at the top of the item (the shared atomic has long returned) and issue the successor's
+// first-needed loads, which then have the edge loop and the epilogue to arrive.
+template <bool PHASE_A>
+__device__ __forceinline__ void wt_next(const Arrays &A, const WtView &V, int lane, size_t tn, const double *g_v,
+                                        int raw, int &wn, WtEarly &En)
+{
+    wn = __shfl_sync(0xffffffffu, raw, 0);
+    if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v, tn);
+}
+
 __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
-                                          const double *g_lo, const WtEarly &E)
+                                          const double *g_lo, const double *g_v, const WtEarly &E, int raw, int &wn,
+                                          WtEarly &En)
 {
     const WtItem I = wt_item(V, wi, lane);
     const int z0 = I.z0, nz = I.nz;
@@ -438,6 +443,7 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
         }
         wt_b1v(E.f0, E.f1, E.f2, p0, p1, m0, m1);
     }
+    wt_next<true>(A, V, lane, tn, g_v, raw, wn, En);
     // ---- the node's edges in ascending edge id: a2/a3 bounds + b1 horizontal ----
 #pragma unroll 2
     for (int k = 0; k < I.cnt; ++k) {
@@ -480,9 +486,11 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
 
 // ---- phase B: one warp item ------------------------------------------------------------------------
 __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
-                                          double *g_vout, double *g_ho, const WtEarly &E)
+                                          const double *g_v, double *g_vout, double *g_ho, const WtEarly &E, int raw,
+                                          int &wn, WtEarly &En)
 {
     const WtItem I = wt_item(V, wi, lane);
+    wt_next<false>(A, V, lane, tn, g_v, raw, wn, En);
     if (!I.out) return;   // ghost slots exist for phase A's stencil only
     const int z0 = I.z0, nz = I.nz;
     const size_t off = tn + I.grow;
@@ -583,7 +591,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
     auto b_ready = [&](int s) { return bar + 8u * (3 * NSTAGE + s); };
     int *next_item = reinterpret_cast<int *>(wt_sm + 8 * 4 * NSTAGE);
     int *tile_of = next_item + NSTAGE;   // (tile, tracer) index staged in each stage, -1: no more work
-    static_assert(8 * 4 * NSTAGE + 8 * NSTAGE <= WT_SMEM_HEAD && NSTAGE <= 4, "smem head");
+    int *tracer_of = tile_of + NSTAGE;   // its tracer (one integer division per tile, not one per warp)
+    static_assert(8 * 4 * NSTAGE + 12 * NSTAGE <= WT_SMEM_HEAD && NSTAGE <= 4, "smem head");
     const int total = T.ntiles * ntracers;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -624,6 +633,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             if (lane == 0) {
                 next_item[s] = 0;
                 tile_of[s] = v;
+                tracer_of[s] = v / T.ntiles;
                 mbar_expect_tx(b_blob(s), (b1 - b0) * 16u);
                 bulk_g2s(smem_u32(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes), T.blob + b0, (b1 - b0) * 16u, b_blob(s));
             }
@@ -641,9 +651,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
             mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1);
-            const int v = tile_of[s];
-            if (v < 0) break;
-            const int tr = v / T.ntiles;
+            if (tile_of[s] < 0) break;
+            const int tr = tracer_of[s];
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             // the transaction count may run negative until this arrives; the phase cannot complete before
             if (warp == 1 && lane == 0)
@@ -684,35 +693,34 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         }
     } else {
         // ---- consumers ----
-        auto grab = [&](int s) {
+        auto draw = [&](int s) {   // lane 0 only; broadcast with __shfl_sync when needed
             int wi = 0;
-            if (lane == 0) wi = atomicAdd(next_item + s, 1);
-            return __shfl_sync(0xffffffffu, wi, 0);
+            if (lane == 0) wi = smem_fetch_add(next_item + s);
+            return wi;
         };
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
             mbar_wait(b_blob(s), (it / NSTAGE) & 1);
-            const int v = tile_of[s];
-            if (v < 0) break;
-            const int tr = v / T.ntiles;
+            if (tile_of[s] < 0) break;
+            const int tr = tracer_of[s];
             mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             const size_t tn = tr * A.ts_node;
             const double *g_v = A.adf_v + tr * A.ts_nodev;
-            // two items ahead: the index after next is drawn (shared atomic + shuffle) and the next
-            // item's first-needed values are loaded while the current item is computed
-            int wi = grab(s), wn = grab(s);
+            // one item ahead: lane 0 draws the next index at the top of an item; the item broadcasts
+            // it and loads the successor's first-needed values before its own edge loop
+            int wi = __shfl_sync(0xffffffffu, draw(s), 0);
             WtEarly E;
             if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v, tn);
             while (wi < V.n_witems) {
                 WtEarly En;
-                if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v, tn);
-                int raw = 0;   // lane 0 draws now; the broadcast waits until the item is done
-                if (lane == 0) raw = atomicAdd(next_item + s, 1);
-                if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, E);
-                else wt_item_b(A, V, wi, lane, tn, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E);
+                int wn = 0;
+                const int raw = draw(s);
+                if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, g_v, E, raw, wn, En);
+                else
+                    wt_item_b(A, V, wi, lane, tn, g_v, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E, raw,
+                              wn, En);
                 wi = wn;
-                wn = __shfl_sync(0xffffffffu, raw, 0);
                 E = En;
             }
             __syncwarp();
