@@ -201,7 +201,7 @@ def run_product(args):
     # ---------------- value: device-resident fused step ----------------
     plan = harness.DevicePlan(m)
     # the packed level storage is the fast path's own layout (plain triangulations)
-    df = harness.DeviceFields(plan, 1, with_uv=False, packed=(plan.kernels == "warp"))
+    df = harness.DeviceFields(plan, 1, with_uv=False, packed=plan.packed_ok)
     df.upload(f, outputs=False)
     halo = None
     if world > 1:
@@ -237,8 +237,8 @@ def run_product(args):
     algA = 8 * (8 * Sn + Sg) + 16 * m.myDim_nod2D
     algB = 8 * (13 * Sn + 2 * Sg)
     kern = {}
-    suffix = {"warp": "_warp", "tile": "_tile", "untiled": ""}[plan.kernels]
-    mode_name = {"warp": "persistent TMA-staged warp-item fused phases A+B, packed level storage", "tile": "tile-staged fused phases A+B",
+    suffix = {"warp": "_warp", "tile": "_tile", "untiled": ""}["warp" if plan.packed_ok else plan.kernels]
+    mode_name = {"warp": "persistent TMA-staged warp-item fused phases A+B, " + ("packed level storage" if plan.packed_ok else "padded rows"), "tile": "tile-staged fused phases A+B",
                  "untiled": "untiled fused phases A+B"}[plan.kernels]
     if world == 1:
         for base, alg in (("phaseA", algA), ("phaseB", algB)):

@@ -401,22 +401,25 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         std::fprintf(stderr, "fesom2-accelerate: too many (tile, tracer) pairs for one launch\n");
         return false;
     }
-    // device-wide tile counters: a ring of self-rearming pairs, one per launch in flight
-    static int *ctr_ring = nullptr;
+    // device-wide tile counters: per device a ring of self-rearming pairs, one per launch in flight
+    static std::map<int, int *> ctr_rings;
     static std::atomic<unsigned> ctr_next{0};
     constexpr unsigned CTR_SLOTS = 256;
     int *ctr = nullptr;
     if (env_int("FCT_WT_DYNAMIC", 1)) {
         static std::mutex ring_mutex;
         std::lock_guard<std::mutex> lock(ring_mutex);
-        if (!ctr_ring) {
-            if (!cuda_ok(cudaMalloc(&ctr_ring, CTR_SLOTS * 2 * sizeof(int)), "cudaMalloc(counters)") ||
-                !cuda_ok(cudaMemset(ctr_ring, 0, CTR_SLOTS * 2 * sizeof(int)), "cudaMemset(counters)")) {
-                ctr_ring = nullptr;
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        int *&ring = ctr_rings[dev_id];
+        if (!ring) {
+            if (!cuda_ok(cudaMalloc(&ring, CTR_SLOTS * 2 * sizeof(int)), "cudaMalloc(counters)") ||
+                !cuda_ok(cudaMemset(ring, 0, CTR_SLOTS * 2 * sizeof(int)), "cudaMemset(counters)")) {
+                ring = nullptr;
                 return false;
             }
         }
-        ctr = ctr_ring + 2 * (ctr_next.fetch_add(1) % CTR_SLOTS);
+        ctr = ring + 2 * (ctr_next.fetch_add(1) % CTR_SLOTS);
     }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
     v.fn<<<grid, (v.issuers + 1 + (isA ? WT_CONVERTERS : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);

@@ -165,11 +165,12 @@ void fct_ale_plan_destroy_(void **plan, int *istat)
     if (plan) *plan = nullptr;
 }
 
-void fct_ale_plan_kernels_(void **plan, int *warp_tiles, int *staged_tiles)
+void fct_ale_plan_kernels_(void **plan, int *warp_tiles, int *staged_tiles, int *packed_tiles)
 {
     Plan *p = P_(plan);
     *warp_tiles = (p && p->wtiles_ok) ? 1 : 0;
     *staged_tiles = (p && p->tiles_ok) ? 1 : 0;
+    *packed_tiles = (p && p->wtiles_pk_ok) ? 1 : 0;
 }
 
 void fct_ale_plan_pitch_(void **plan, int *pitch)

@@ -52,6 +52,9 @@ struct WarpTilesDev {
 // warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A NPW+1 the a1 converter, then NWC consumers
 // (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128, 20 -> 96, 24 -> 80)
 constexpr int WT_SMEM_HEAD = 256;     // mbarriers + item counters in front of the stages
+#ifndef WT_IDLE_NS
+#define WT_IDLE_NS 400
+#endif
 constexpr int WT_CONVERTERS = 2;      // phase A: warps that turn the landed rows into the a1 bounds
 constexpr int WT_SMEM_MAX = 227 * 1024;
 // blob header: 16 ints
@@ -113,7 +116,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "}" ::"r"(bar), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+// producer-side wait: producers are idle most of the time; probe, then sleep between probes so that
+// they leave the issue slots to the consumers (costs a fraction of a microsecond per hand-over)
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(WT_IDLE_NS);
+    }
+}
 
 // lane 0's draw from a shared-memory counter (the C++ atomicAdd carries warp-aggregation code for
 // a uniform address that a single active lane does not need)

@@ -164,9 +164,10 @@ class DevicePlan:
         p = C.c_int()
         self.lib.fct_ale_plan_pitch_(C.byref(self.h), C.byref(p))
         self.pitch = p.value
-        wt, tt = C.c_int(), C.c_int()
-        self.lib.fct_ale_plan_kernels_(C.byref(self.h), C.byref(wt), C.byref(tt))
+        wt, tt, pk = C.c_int(), C.c_int(), C.c_int()
+        self.lib.fct_ale_plan_kernels_(C.byref(self.h), C.byref(wt), C.byref(tt), C.byref(pk))
         self.kernels = "warp" if wt.value else ("tile" if tt.value else "untiled")
+        self.packed_ok = bool(pk.value)
 
     def free(self):
         st = C.c_int()

@@ -202,8 +202,9 @@ void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *myDim_elem2D,
                            int *which, int *packed, long long *blob_capacity, unsigned *blob, int *tiles_capacity,
                            unsigned *blob_off, int *ntiles, int *smem_bytes, int *istat);
 /* which fused kernels *mode 1 of fct_ale_step_ will run on this plan: the persistent TMA-staged
- * warp-item kernels (*warp_tiles), else the tile-staged ones (*staged_tiles), else the untiled */
-void fct_ale_plan_kernels_(void **plan, int *warp_tiles, int *staged_tiles);
+ * warp-item kernels (*warp_tiles), else the tile-staged ones (*staged_tiles), else the untiled;
+ * *packed_tiles: fct_ale_fields_create_packed_ is available */
+void fct_ale_plan_kernels_(void **plan, int *warp_tiles, int *staged_tiles, int *packed_tiles);
 /* pitch (in doubles) of every padded device row of this plan: nl rounded up to a multiple of 8
  * (64 bytes), so that no DRAM sector is shared by two rows */
 void fct_ale_plan_pitch_(void **plan, int *pitch);
