@@ -283,7 +283,7 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
     auto need_bytes = [&](size_t nrows, size_t nerows, size_t nn, size_t nent, size_t nsched, int rb, int eb) {
         const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + nn * 16 + nent * 16 +
                             pad16((int)((nsched + W - 1) / W * W) * 2);
-        return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack;
+        return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack + 256;   // + the schedule's re-ordering margin
     };
 
     int pos = 0, tile = 0;
@@ -433,10 +433,21 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
                                       (FCT_META_SECOND(e.z) ? 0x80000000u : 0u);
                 ent.push_back(make_int4(esoff[e.x], nsoff[e.y], (int)meta, (int)egoff(e.x)));
             }
-            size_t len = sched.size();
-            schedule_node(&sched, len, i, (nz + 1) / 2);
             out.slots += (nz + 1) / 2;
             out.edge_uses += e1 - e0;
+        }
+        {
+            // the lanes of a warp item walk their nodes' edge lists in lockstep: schedule nodes of
+            // equal degree next to each other so that no lane idles through another node's longer list
+            std::vector<int> order((size_t)nn);
+            for (int i = 0; i < nn; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+                return d.edg_off[tile_nodes[x] + 1] - d.edg_off[tile_nodes[x]] > d.edg_off[tile_nodes[y] + 1] - d.edg_off[tile_nodes[y]];
+            });
+            for (int i : order) {
+                size_t len = sched.size();
+                schedule_node(&sched, len, i, (std::max(nlev_n[tile_nodes[i]] - 1, 0) + 1) / 2);
+            }
         }
         sched.resize((sched.size() + W - 1) / W * W, (unsigned short)WT_IDLE);
         // ---- 4. assemble the blob ----
