@@ -9,28 +9,35 @@
 // runs ahead of the arithmetic:
 //
 //   * A tile is a run of consecutive owned nodes.  Its plan data is ONE contiguous blob: header,
-//     table of node rows to stage, table of edge-flux rows to stage, one header per node, the
-//     nodes' edge entries with precomputed shared-memory BYTE offsets, and a warp-item schedule.
-//   * One persistent CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through an
-//     NSTAGE-deep ring of shared-memory stages guarded by mbarriers.  Producer warps feed the ring
-//     with the TMA unit (cp.async.bulk, SASS UBLKCP): warp 0 fetches the blob; NPW issuer warps
-//     share the tile's copy list -- one bulk copy per staged row, exactly the active levels in
-//     16-byte granules: the node rows of the two gathered arrays (phase A: fct_LO and ttf; phase
-//     B: fct_plus and fct_minus) and the edge-flux rows (every edge with both ends in the tile is
-//     fetched once, not once per end) -- a single warp cannot issue them fast enough
-//     (profiles/r1_v3_*); in phase A one more warp turns the landed (fct_LO, ttf) rows in place
-//     into the a1 bounds of reference.cpp:315-316.  NWC consumer warps pull warp items of the
-//     ready stage from a shared counter, so tiles k+1 and k+2 are in flight while tile k is
-//     computed, and each consumer loads the first-needed own-column values of its NEXT item while
-//     it works on the current one.
+//     list of bulk copies, one header per node, the nodes' edge entries with precomputed
+//     shared-memory BYTE offsets, and a warp-item schedule.  The same kernels serve the padded
+//     layout (row = index * pitch) and the packed level storage (columns back to back, active
+//     levels only): every global offset they use comes out of the blob.
+//   * One persistent CTA per SM draws tiles from a device-wide counter (in curve order: the tiles
+//     in flight are a compact patch, the tail is balanced) and runs them through an NSTAGE-deep
+//     ring of shared-memory stages guarded by mbarriers.  Producer warps feed the ring with the TMA
+//     unit (cp.async.bulk, SASS UBLKCP): warp 0 fetches the blob (prefetched into L2 while the
+//     stage is still busy); NPW issuer warps share the tile's copy list: the columns of the two
+//     gathered node arrays (phase A: fct_LO and ttf; phase B: fct_plus and fct_minus; own + halo
+//     nodes) and the tile's edge-flux rows (an edge with both ends in the tile is fetched once, not
+//     once per end), exactly the active levels in 16-byte granules.  The stage is laid out own
+//     columns first, halo columns, edge rows by ascending id, so rows that are adjacent in global
+//     memory are adjacent in shared memory and travel as ONE copy: about 40 copies per tile in the
+//     packed storage, 240 in the padded layout, where a single issuer warp was the bottleneck
+//     (profiles/r1_v3_*).  In phase A two more warps turn the landed (fct_LO, ttf) rows in place
+//     into the a1 bounds of reference.cpp:315-316.  NWC consumer warps draw warp items of the ready
+//     stage from a shared counter, so tiles k+1 and k+2 are in flight while tile k is computed, and
+//     every item loads the first-needed own-column values of the warp's NEXT item before its own
+//     edge loop.
 //   * A warp item is 32 lanes, each a (node, pair of ACTIVE levels) slot; consecutive lanes hold
 //     consecutive slots of a node, so the vertical 3-point stencil of a3 is two warp shuffles.  A
 //     column that does not fit the rest of an item is split, with one GHOST slot on either side of
 //     the cut (it recomputes the neighbouring cluster bound and stores nothing), which keeps the
-//     lanes > 90 % full at any depth.
+//     lanes > 90 % full at any depth.  Nodes of equal degree are scheduled next to each other, so
+//     the lanes of an item walk edge lists of equal length.
 //   * In the item loop every shared-memory address is "region base + precomputed offset + 8*z0",
-//     level masks ride on the DSETP...AND predicates, the +/- split of b1 horizontal is a
-//     predicated sum (adding +0 is exact, and the sums never are -0).
+//     level masks ride on the DSETP...AND predicates, the +/- split of b1 horizontal runs on the
+//     FP64 pipe (adding +0 is exact, and the sums never are -0).
 //
 // Arithmetic and its order are those of fct_kernels.cuh (bit-identical results).
 #pragma once
@@ -45,27 +52,31 @@ struct WarpTilesDev {
     const uint4 *blob;          // concatenated per-tile blobs
     const unsigned *blob_off;   // [ntiles+1] in 16-byte units
     int ntiles;
-    int smem_bytes;             // dynamic shared memory of one CTA (max over tiles)
+    int smem_bytes;             // shared memory of one stage (max over tiles)
     int diag;                   // timing experiments only (wrong results): 1 skip the edge-row copies, 2 skip all row copies
 };
 
-// warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A NPW+1 the a1 converter, then NWC consumers
-// (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128, 20 -> 96, 24 -> 80)
-constexpr int WT_SMEM_HEAD = 256;     // mbarriers + item counters in front of the stages
+// warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A WT_CONVERTERS a1 converters, then NWC
+// consumers (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128 per
+// thread, 20 -> 96, 24 -> 80)
+constexpr int WT_SMEM_HEAD = 256;     // mbarriers + per-stage counters in front of the stages
 #ifndef WT_IDLE_NS
-#define WT_IDLE_NS 400
+#define WT_IDLE_NS 400                // sleep of an idle producer between two probes of its barrier
 #endif
 constexpr int WT_CONVERTERS = 2;      // phase A: warps that turn the landed rows into the a1 bounds
 constexpr int WT_SMEM_MAX = 227 * 1024;
 // blob header: 16 ints
-//  [0] node rows  [1] edge rows  [2] nodes  [3] warp items
-//  [4] byte offset of the edge-row table  [5] of the node headers  [6] of the entries  [7] of the schedule
-//  [8] blob bytes  [9] bytes of ONE staged node-row region  [10] bytes of the edge-row region  [11] bytes the row copies deliver
-// schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
-// node-row table at byte 64: int2 {global element offset of the row, (16-byte units) smem offset | size << 16}
-// node header int4: {node*pitch, nz | fillmin << 8 | self depth << 16, smem byte offset of the own row, first entry | entries << 16}
+//  [0] bulk copies  [1] edge rows  [2] nodes  [3] warp items
+//  [4] node rows  [5] byte offset of the node headers  [6] of the entries  [7] of the schedule
+//  [8] blob bytes  [9] bytes of ONE staged node-row region  [10] bytes of the edge-row region  [11] bytes the copies deliver
+// copy list at byte 64: int2 {global element offset of the first row,
+//     (16-byte units) smem offset from the first row region | size << 14 | array << 28} with array 0 / 1
+//     the two gathered node arrays (regions A, B) and 2 the edge fluxes (region E); regions are consecutive
+// node header int4: {global element offset of the column, nz | fillmin << 8 | self depth << 16,
+//                    smem byte offset of the own row, first entry | entries << 16}
 // entry int4: {smem byte offset of the edge row, smem byte offset of the other node's row,
-//              depth | writer << 30 | second << 31, edge*pitch}
+//              depth | writer << 30 | second << 31, global element offset of the edge row}
+// schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
 constexpr int WT_HDR_BYTES = 64;
 constexpr unsigned WT_IDLE = 0xffffu;
 
