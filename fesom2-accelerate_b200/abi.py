@@ -27,7 +27,7 @@ SYMBOLS = [
     "fct_ale_event_elapsed_ms_", "fct_ale_event_destroy_", "fct_ale_mem_info_",
     "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_", "fct_ale_plan_inspect_", "fct_ale_plan_kernels_",
     "fct_ale_fields_create_", "fct_ale_fields_create_packed_", "fct_ale_fields_destroy_", "fct_ale_field_upload_",
-    "fct_ale_field_download_", "fct_ale_step_", "fct_ale_stage_",
+    "fct_ale_field_download_", "fct_ale_field_link_bytes_", "fct_ale_step_", "fct_ale_stage_",
     "fct_ale_comm_unique_id_", "fct_ale_halo_create_", "fct_ale_halo_destroy_",
     "fct_ale_halo_exchange_",
 ]
@@ -40,7 +40,7 @@ STAGE_IDS = dict(a1=0, a2=1, a3=2, b1v=3, b1h=4, b2=5, b3v=6, b3h=7, cv=8, ch=9,
                  phaseB=11, phaseA_tile=12, phaseB_tile=13, phaseA_tile_boundary=14,
                  phaseA_tile_interior=15, phaseB_tile_boundary=16, phaseB_tile_interior=17,
                  phaseA_warp=18, phaseB_warp=19, phaseA_warp_boundary=20, phaseA_warp_interior=21,
-                 phaseB_warp_boundary=22, phaseB_warp_interior=23)
+                 phaseB_warp_boundary=22, phaseB_warp_interior=23, b1h_atomic=24, ch_atomic=25)
 
 
 class GpuMemory(C.Structure):

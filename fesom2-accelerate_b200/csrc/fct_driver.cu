@@ -73,6 +73,8 @@ static kern_t kernel_of(int stage)
     case ST_CH: return k_ch<VEC>;
     case ST_PHASE_A: return k_phaseA<VEC>;
     case ST_PHASE_B: return k_phaseB<VEC>;
+    case ST_B1H_ATOMIC: return k_b1h_atomic<VEC>;
+    case ST_CH_ATOMIC: return k_ch_atomic<VEC>;
     }
     return nullptr;
 }
@@ -203,6 +205,7 @@ static int env_int(const char *name, int dflt)
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
+int tune_int(const char *name, int dflt) { return env_int(name, dflt); }
 void set_tune(const char *name, int value)
 {
     std::lock_guard<std::mutex> lock(g_tune_mutex);

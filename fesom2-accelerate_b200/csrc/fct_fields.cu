@@ -125,6 +125,49 @@ __global__ void k_unpack_columns(double *__restrict__ dst, const double *__restr
     }
 }
 
+// Measured alternative (knob FCT_DIRECT_COPY=1): the same two movements straight between PAGE-LOCKED
+// host memory and the packed columns, one warp per row: the SMs read / write the host array over
+// PCIe themselves (mapped, zero-copy), so only the levels that have a slot cross the link on the
+// way up (the inactive 30 % of a dense array stay behind) and no dense staging copy exists in HBM.
+// Measured on B200 (gpurun_out/s3_e2e_copy.log): SM-issued PCIe reads stop at 35 GB/s of useful
+// bytes against 54 GB/s for the copy engine's dense copy (37 GB/s useful), so the staged copy stays
+// the default; the direct path is for callers short of HBM.
+__global__ void k_pack_columns_direct(double *__restrict__ dst, const double *__restrict__ host,
+                                      const unsigned *__restrict__ col, size_t rows, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nw) {
+        const unsigned c0 = __ldg(col + r);
+        const int n = min((int)(__ldg(col + r + 1) - c0), W);
+        const double *src = host + r * (size_t)W;
+        for (int c = lane; c < n; c += 32) dst[c0 + c] = __ldcs(src + c);
+    }
+}
+__global__ void k_unpack_columns_direct(double *__restrict__ host, const double *__restrict__ src,
+                                        const unsigned *__restrict__ col, size_t rows, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nw) {
+        const unsigned c0 = __ldg(col + r);
+        const int n = min((int)(__ldg(col + r + 1) - c0), W);
+        double *dst = host + r * (size_t)W;
+        for (int c = lane; c < W; c += 32) __stcs(dst + c, c < n ? src[c0 + c] : 0.);
+    }
+}
+
+// device alias of a page-locked (cudaMallocHost / cudaHostRegister) host pointer, else null
+static double *mapped_alias(const void *host)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? static_cast<double *>(at.devicePointer) : nullptr;
+}
+
 static bool run_stage(Fields *f, const Arrays &A, int stage, const int *list, int first, int count, cudaStream_t s)
 {
     return launch_stage(stage, 2, A, f->plan->dev, list, first, count, f->T, s);
@@ -262,6 +305,18 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
         return;
     }
     cudaStream_t st = S_(stream);
+    if (f->packed && tune_int("FCT_DIRECT_COPY", 0) != 0) {
+        if (double *alias = mapped_alias(host)) {
+            const unsigned *col = m.kind == ROW_EDGE ? f->plan->d_ecol : f->plan->d_ncol;
+            const int W = (int)(width / sizeof(double));
+            const int blocks = (int)std::min<size_t>((rows + 7) / 8, (size_t)148 * 16);
+            if (up) k_pack_columns_direct<<<blocks, 256, 0, st>>>(d, alias, col, rows, W);
+            else k_unpack_columns_direct<<<blocks, 256, 0, st>>>(alias, d, col, rows, W);
+            count_launch(1);
+            *istat = cuda_ok(cudaGetLastError(), "direct pack") ? 0 : 1;
+            return;
+        }
+    }
     if (!f->packed && width == pitch) {
         cudaError_t e = up ? cudaMemcpyAsync(d, host, rows * pitch, cudaMemcpyHostToDevice, st)
                            : cudaMemcpyAsync(host, d, rows * pitch, cudaMemcpyDeviceToHost, st);
@@ -304,6 +359,22 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
     *istat = ok ? 0 : 1;
 }
 
+void fct_ale_field_link_bytes_(void **fields, int *field, real_type *host, int *upload, long long *bytes)
+{
+    *bytes = 0;
+    Fields *f = F_(fields);
+    if (!f || *field < 0 || *field >= FCT_FIELD_COUNT || !f->buf[*field] || !host) return;
+    const FieldMeta m = meta_of(*field);
+    const size_t rows = field_rows(f, m.kind);
+    const size_t W = (size_t)(f->plan->nl - m.width_minus) * (*field == FCT_UV_RHS ? 2 : 1);
+    *bytes = (long long)(rows * W * sizeof(double));
+    if (!(f->packed && *upload && tune_int("FCT_DIRECT_COPY", 0) != 0 && mapped_alias(host))) return;
+    const std::vector<unsigned> &col = m.kind == ROW_EDGE ? f->plan->ecol : f->plan->ncol;
+    long long n = 0;
+    for (size_t r = 0; r < rows; ++r) n += (long long)std::min<size_t>(col[r + 1] - col[r], W);
+    *bytes = n * (long long)sizeof(double);
+}
+
 void fct_ale_field_upload_(void **fields, int *field, int *tracer, real_type *host, void **stream, int *istat)
 {
     field_copy(fields, field, tracer, host, stream, istat, true);
@@ -322,7 +393,8 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     if (!f) return;
     const Plan *p = f->plan;
     const int st = *stage;
-    const Arrays A = arrays_of(f, st >= ST_PHASE_A ? 1 : 0, *dt, *flux_eps, *bignumber);
+    const Arrays A = arrays_of(f, (st >= ST_PHASE_A && st < ST_B1H_ATOMIC) ? 1 : 0, *dt, *flux_eps, *bignumber);
+    if (st < 0 || st > ST_CH_ATOMIC) return;
     if (f->packed && !(st >= ST_PHASE_A_WARP && st <= 23)) {
         std::fprintf(stderr, "fesom2-accelerate: packed fields run the warp-item kernels only (stages 18-23)\n");
         return;
@@ -362,7 +434,7 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     int count = p->N;
     if (st == ST_A1) count = p->N + p->H;
     else if (st == ST_A2) count = p->E;
-    else if (st == ST_B3H) count = p->G;
+    else if (st == ST_B3H || st == ST_B1H_ATOMIC || st == ST_CH_ATOMIC) count = p->G;
     if (st == ST_A2 || st == ST_A3) {
         if (!f->buf[FCT_UV_RHS]) {
             std::fprintf(stderr, "fesom2-accelerate: stage %d needs fields created with UV_rhs\n", st);

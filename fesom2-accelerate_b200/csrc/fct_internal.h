@@ -10,11 +10,14 @@ namespace fct {
 enum Stage {
     ST_A1 = 0, ST_A2 = 1, ST_A3 = 2, ST_B1V = 3, ST_B1H = 4, ST_B2 = 5, ST_B3V = 6, ST_B3H = 7,
     ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11, ST_PHASE_A_TILE = 12, ST_PHASE_B_TILE = 13,
-    ST_PHASE_A_WARP = 18, ST_PHASE_B_WARP = 19
+    ST_PHASE_A_WARP = 18, ST_PHASE_B_WARP = 19,
+    ST_B1H_ATOMIC = 24, ST_CH_ATOMIC = 25   // measured alternatives (fp64 atomics), never on the product path
 };
 
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(int n);
+// tuning knob FCT_<...> (fct_ale_tune_ or the environment), full name with the FCT_ prefix
+int tune_int(const char *name, int dflt);
 bool launch_stage(int stage, int vec, const Arrays &A, const MeshDev &M, const int *list, int first,
                   int count, int ntracers, cudaStream_t s);
 // tile-staged fused phase (stage = ST_PHASE_A / ST_PHASE_B) over node set `which`:

@@ -500,6 +500,63 @@ __global__ void k_ch(Arrays A, MeshDev M, const int *list, int first, int count)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Measured alternative only: the reference's edge-centric scatter with fp64 atomics (RED.ADD.F64 on
+// sm_100a).  Summation order depends on the schedule, so results are NOT bit-reproducible (parity
+// within 1e-12 relative); the product path never launches these, tools/stage_sweep.py times them
+// next to the gathers.
+// ------------------------------------------------------------------------------------------------
+
+// b1 horizontal as kernels/fct_ale_b1_horizontal.cu:3-29 -- 4 atomics per edge level
+template <int VEC>
+__global__ void k_b1h_atomic(Arrays A, MeshDev M, const int *list, int first, int count)
+{
+    const Item it = my_item(list, first, count, VEC);
+    if (it.idx < 0) return;
+    const int g = it.idx;
+    const int dg = edge_depth_dev(M, g);
+    if (it.z0 >= dg) return;
+    const size_t tb = blockIdx.y * A.ts_node + it.z0;
+    const size_t r1 = tb + (size_t)(__ldg(M.edges + 2 * g) - 1) * A.pitchL;
+    const size_t r2 = tb + (size_t)(__ldg(M.edges + 2 * g + 1) - 1) * A.pitchL;
+    double h[VEC];
+    ldv_ro<VEC>(A.adf_h_in + blockIdx.y * A.ts_edge + (size_t)g * A.pitchH + it.z0, h);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        if (it.z0 + v < dg) {
+            atomicAdd(A.plus + r1 + v, pick_max(0., h[v]));
+            atomicAdd(A.minus + r1 + v, pick_min(0., h[v]));
+            atomicAdd(A.plus + r2 + v, pick_max(0., -h[v]));
+            atomicAdd(A.minus + r2 + v, pick_min(0., -h[v]));
+        }
+    }
+}
+
+// c horizontal as kernels/fct_ale_c_horizontal.cu:3-28 -- 2 atomics and 2 divisions per edge level
+template <int VEC>
+__global__ void k_ch_atomic(Arrays A, MeshDev M, const int *list, int first, int count)
+{
+    const Item it = my_item(list, first, count, VEC);
+    if (it.idx < 0) return;
+    const int g = it.idx;
+    const int dg = edge_depth_dev(M, g);
+    if (it.z0 >= dg) return;
+    const int n1 = __ldg(M.edges + 2 * g) - 1, n2 = __ldg(M.edges + 2 * g + 1) - 1;
+    const size_t r1 = blockIdx.y * A.ts_node + (size_t)n1 * A.pitchL + it.z0;
+    const size_t r2 = blockIdx.y * A.ts_node + (size_t)n2 * A.pitchL + it.z0;
+    double h[VEC];
+    ldv<VEC>(A.adf_h_out + blockIdx.y * A.ts_edge + (size_t)g * A.pitchH + it.z0, h);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        if (it.z0 + v < dg) {
+            const double a1 = __ldg(A.area + (size_t)n1 * A.pitchV + it.z0 + v);
+            const double a2 = __ldg(A.area + (size_t)n2 * A.pitchV + it.z0 + v);
+            atomicAdd(A.del_h + r1 + v, h[v] * (A.dt / a1));
+            atomicAdd(A.del_h + r2 + v, -(h[v] * (A.dt / a2)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused phase kernels (docs/fct_ale_dependencies.dot: the only global dependency inside the chain
 // is the neighbours' fct_plus / fct_minus between b2 and b3 horizontal).
 // ------------------------------------------------------------------------------------------------

@@ -352,8 +352,17 @@ class DeviceFields:
         self.stream.sync()
         return st
 
+    def link_bytes(self, name: str, host: np.ndarray, upload: bool) -> int:
+        """Bytes that cross PCIe for this field and host array (the library's own count: the dense
+        array, or only the slots of the packed storage when the host array is page-locked)."""
+        n = C.c_longlong()
+        self.lib.fct_ale_field_link_bytes_(C.byref(self.h), ci(abi.FIELD_IDS[name]), dptr(host.reshape(-1)),
+                                           ci(1 if upload else 0), C.byref(n))
+        return n.value
+
     def host_step_bytes(self, f: Fields):
-        return (sum(getattr(f, k).nbytes for k in self.STEP_INPUTS), sum(getattr(f, k).nbytes for k in self.STEP_RESULTS))
+        return (sum(self.link_bytes(k, getattr(f, k), True) for k in self.STEP_INPUTS),
+                sum(self.link_bytes(k, getattr(f, k), False) for k in self.STEP_RESULTS))
 
     def stage(self, name: str, f: Fields, sync: bool = True):
         st = C.c_int()

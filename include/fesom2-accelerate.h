@@ -231,10 +231,20 @@ enum fct_field_id {
 /* dense host array (the Fortran layout above) <-> padded device rows of tracer *tracer
  * (mesh-static fields area / area_inv / hnode / hnode_new ignore *tracer).  Asynchronous on
  * *stream; host memory should be pinned for the copy to overlap. */
+/* The copy is one contiguous PCIe copy through a dense staging buffer plus a repack kernel.
+ * Measured alternative for packed fields and PAGE-LOCKED host arrays (allocate_pinned_doubles_,
+ * cudaHostRegister), tuning knob "DIRECT_COPY" 1: one kernel reads / writes the host array over
+ * PCIe itself (mapped memory), so an upload moves only the levels that have a slot (about 70 % of
+ * a dense array) and no staging buffer exists; SM-issued PCIe reads reach 35 GB/s against the copy
+ * engine's 54 GB/s on B200, so it saves memory, not time. */
 void fct_ale_field_upload_(void **fields, int *field, int *tracer, real_type *host, void **stream,
                            int *istat);
 void fct_ale_field_download_(void **fields, int *field, int *tracer, real_type *host, void **stream,
                              int *istat);
+
+/* bytes that cross the host link when `field` is uploaded from (*upload != 0) or downloaded to
+ * `host`: the dense array, or only the slots of the packed storage on the direct path */
+void fct_ale_field_link_bytes_(void **fields, int *field, real_type *host, int *upload, long long *bytes);
 
 /* One fct_ale step a1..c over all tracers of `fields`, everything resident on the device.
  *   *mode 0: ten stage kernels (one per reference kernel);  *mode 1: two fused phase kernels, the
@@ -252,7 +262,10 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
 /* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,
  * 6 b3v, 7 b3h, 8 c_v, 9 c_h; 10 fused phase A, 11 fused phase B; 12 / 13 the tile-staged
  * fused phases (14-17: their boundary / interior subsets); 18 / 19 the warp-item fused phases
- * (20 / 21: phase A on the boundary / interior tiles, 22 / 23: phase B) */
+ * (20 / 21: phase A on the boundary / interior tiles, 22 / 23: phase B);
+ * 24 / 25: b1h / c_h as the reference's edge-centric fp64 atomicAdd scatter
+ * (kernels/fct_ale_b1_horizontal.cu:24-27, fct_ale_c_horizontal.cu:25-26) -- a measured
+ * alternative only: not bit-reproducible, never launched by fct_ale_step_ or the *_acc_ calls */
 void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, real_type *flux_eps,
                     real_type *bignumber, int *istat);
 

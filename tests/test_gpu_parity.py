@@ -167,6 +167,47 @@ def test_host_resident_steps(mesh_mod, harness, oracle_mod, packed):
     plan.free()
 
 
+@pytest.mark.parametrize("direct", [1, 0])
+def test_packed_copies_from_page_locked_memory(mesh_mod, harness, abi, oracle_mod, direct):
+    """Page-locked host arrays: with DIRECT_COPY=1 packed uploads / downloads run as one kernel over
+    mapped host memory (only the levels that have a slot cross PCIe); the default is the staged copy.
+    Both give the oracle's bits, and a download writes zeros into the levels that have no slot."""
+    m, f0 = cases(mesh_mod, "deep")
+    want = f0.copy()
+    oracle_mod.fct_ale(m, want)
+    f = f0.copy()
+    for k, v in list(f.__dict__.items()):
+        if isinstance(v, np.ndarray) and v.dtype == np.float64:
+            p = abi.pinned_empty(v.shape)
+            p[...] = v
+            setattr(f, k, p)
+    try:
+        abi.tune("DIRECT_COPY", direct)
+        plan = harness.DevicePlan(m)
+        df = harness.DeviceFields(plan, 1, packed=True)
+        df.upload(f)
+        up, dn = df.host_step_bytes(f)
+        dense_up = sum(getattr(f, k).nbytes for k in df.STEP_INPUTS)
+        assert (up < 0.9 * dense_up) if direct else (up == dense_up)
+        assert dn == sum(getattr(f, k).nbytes for k in df.STEP_RESULTS)
+        out = f.copy()
+        for k in df.STEP_RESULTS:
+            p = abi.pinned_empty(getattr(f, k).shape)
+            p[...] = np.nan
+            setattr(out, k, p)
+        assert df.host_steps(f, out, 2, mode=1) == 10
+        act = np.arange(m.L)[None, :] < (m.nlevels_nod2D[:, None] - 1)
+        for k in df.STEP_RESULTS:
+            got = getattr(out, k)
+            assert bits_equal(got[act], getattr(want, k)[act]), k
+            assert np.isfinite(got).all(), k
+        check(df.download(f, mode=1), want)
+        df.free()
+        plan.free()
+    finally:
+        abi.tune("DIRECT_COPY", 0)
+
+
 def test_stage_by_stage(mesh_mod, harness, oracle_mod):
     """Each stage kernel against the oracle stage it replaces (the reference's NUM_KERNELS staged
     execution, src/fesom2-accelerate.cu:256-335)."""
@@ -181,6 +222,30 @@ def test_stage_by_stage(mesh_mod, harness, oracle_mod):
         got = df.download(f, mode=0)
         check(got, want)
         assert bits_equal(got.UV_rhs, want.UV_rhs), name
+    df.free()
+    plan.free()
+
+
+def test_atomic_alternatives(mesh_mod, harness, oracle_mod):
+    """The reference's edge-centric fp64 atomicAdd scatter for b1h / c_h, kept as a measured
+    alternative (stages 24 / 25): order of summation is the schedule's, so 1e-12, not bits."""
+    m, f = cases(mesh_mod, "pi")
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(f)
+    want = f.copy()
+    swap = {"b1h": "b1h_atomic", "ch": "ch_atomic"}
+    for name, fn in oracle_mod.STAGES:
+        fn(m, want)
+        df.stage(swap.get(name, name), f)
+    got = df.download(f, mode=0)
+    check(got, want, keys=("fct_ttf_max", "fct_ttf_min"))
+    n = m.myDim_nod2D
+    for k in OUT_KEYS[2:]:
+        a, b = getattr(got, k), getattr(want, k)
+        if k != "fct_adf_h":
+            a, b = a[:n], b[:n]
+        assert rel_err(a, b, floor=1.0) <= TOL, k
     df.free()
     plan.free()
 

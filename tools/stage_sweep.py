@@ -46,6 +46,10 @@ for s in ["a1", "a2", "a3", "b1v", "b1h", "b2", "b3v", "b3h", "cv", "ch"]:
     ms = timeit(lambda: df.stage(s, f, sync=False)); tot += ms
     b = model[s] * T
     print(f"| {s} | k_{s}<2> | {ms:.3f} | {b/1e9:.3f} | {b/ms/1e6:.0f} | {b/ms/1e6/65.472:.1f} |")
+for s, d in (("b1h_atomic", "b1h"), ("ch_atomic", "ch")):
+    ms = timeit(lambda: df.stage(s, f, sync=False))
+    b = model[d] * T
+    print(f"| {s} (alternative: edge scatter, fp64 atomicAdd) | k_{s}<2> | {ms:.3f} | {b/1e9:.3f} | {b/ms/1e6:.0f} | {b/ms/1e6/65.472:.1f} |")
 print(f"| staged chain | ten launches | {tot:.3f} | {sum(model.values())*T/1e9:.3f} | {sum(model.values())*T/tot/1e6:.0f} | {sum(model.values())*T/tot/1e6/65.472:.1f} |")
 for s, alg in (("phaseA_warp", algA), ("phaseB_warp", algB)):
     ms = timeit(lambda: df.stage(s, f, sync=False))
