@@ -27,7 +27,7 @@ SYMBOLS = [
     "fct_ale_event_elapsed_ms_", "fct_ale_event_destroy_", "fct_ale_mem_info_",
     "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_", "fct_ale_plan_inspect_", "fct_ale_plan_kernels_",
     "fct_ale_fields_create_", "fct_ale_fields_create_packed_", "fct_ale_fields_destroy_", "fct_ale_field_upload_",
-    "fct_ale_field_download_", "fct_ale_field_link_bytes_", "fct_ale_step_", "fct_ale_stage_",
+    "fct_ale_field_download_", "fct_ale_field_link_bytes_", "fct_ale_step_", "fct_ale_step_general_", "fct_ale_halo_exchange_field_", "fct_ale_stage_",
     "fct_ale_comm_unique_id_", "fct_ale_halo_create_", "fct_ale_halo_destroy_",
     "fct_ale_halo_exchange_",
 ]
@@ -35,12 +35,14 @@ SYMBOLS = [
 # enum fct_field_id
 FIELD_IDS = dict(ttf=0, fct_LO=1, fct_adf_v=2, fct_adf_h=3, area=4, area_inv=5, hnode=6,
                  hnode_new=7, del_ttf_advvert=8, del_ttf_advhoriz=9, fct_ttf_max=10, fct_ttf_min=11,
-                 fct_plus=12, fct_minus=13, UV_rhs=14, fct_adf_h_out=15, fct_adf_v_out=16)
+                 fct_plus=12, fct_minus=13, UV_rhs=14, fct_adf_h_out=15, fct_adf_v_out=16,
+                 fct_adf_v2=17, fct_adf_h2=18)
 STAGE_IDS = dict(a1=0, a2=1, a3=2, b1v=3, b1h=4, b2=5, b3v=6, b3h=7, cv=8, ch=9, phaseA=10,
                  phaseB=11, phaseA_tile=12, phaseB_tile=13, phaseA_tile_boundary=14,
                  phaseA_tile_interior=15, phaseB_tile_boundary=16, phaseB_tile_interior=17,
                  phaseA_warp=18, phaseB_warp=19, phaseA_warp_boundary=20, phaseA_warp_interior=21,
-                 phaseB_warp_boundary=22, phaseB_warp_interior=23, b1h_atomic=24, ch_atomic=25)
+                 phaseB_warp_boundary=22, phaseB_warp_interior=23, b1h_atomic=24, ch_atomic=25,
+                 a3_vlimit2=26, a3_vlimit3=27, b3v_iter=28, b3h_iter=29, lo_update=30)
 
 
 class GpuMemory(C.Structure):

@@ -75,6 +75,11 @@ static kern_t kernel_of(int stage)
     case ST_PHASE_B: return k_phaseB<VEC>;
     case ST_B1H_ATOMIC: return k_b1h_atomic<VEC>;
     case ST_CH_ATOMIC: return k_ch_atomic<VEC>;
+    case ST_A3_VLIMIT2:
+    case ST_A3_VLIMIT3: return k_a3_vlimit<VEC>;
+    case ST_B3V_ITER: return k_b3v_iter<VEC>;
+    case ST_B3H_ITER: return k_b3h_iter<VEC>;
+    case ST_LO_UPDATE: return k_lo_update<VEC>;
     }
     return nullptr;
 }
@@ -88,9 +93,16 @@ bool launch_stage(int stage, int vec, const Arrays &A, const MeshDev &M, const i
     kern_t k = (vec == 2) ? kernel_of<2>(stage) : kernel_of<1>(stage);
     if (!k) return false;
     const Geom g = geom(A.nl, vec);
-    const size_t smem = (stage == ST_A3 || stage == ST_PHASE_A) ? g.smem : 0;
+    const bool a3v = stage == ST_A3_VLIMIT2 || stage == ST_A3_VLIMIT3;
+    const size_t smem = (stage == ST_A3 || stage == ST_PHASE_A || a3v) ? g.smem : 0;
     dim3 grid((count + g.ny - 1) / g.ny, ntracers, 1);
-    k<<<grid, g.block, smem, s>>>(A, M, list, first, count);
+    if (a3v) {
+        Arrays B = A;
+        B.vlimit = stage == ST_A3_VLIMIT2 ? 2 : 3;
+        k<<<grid, g.block, smem, s>>>(B, M, list, first, count);
+    } else {
+        k<<<grid, g.block, smem, s>>>(A, M, list, first, count);
+    }
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "kernel launch");
 }
@@ -351,6 +363,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     }
     WarpTilesDev T = packed ? p->wtiles_pk[which] : p->wtiles[which];
     T.diag = env_int("FCT_WT_DIAG", 0);
+    T.opt = env_int("FCT_WT_OPT", 2);   // measured (gpurun_out/s6_sweep_mid.log): 2 is +10 % on phase A, 1 neutral
     if (T.ntiles <= 0) return true;
     if (!packed && (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch)) {
         std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");
@@ -715,8 +728,9 @@ void fct_ale_pre_comm_acc_(int *alg_state, void **s, void **fct_ttf_max, void **
     *alg_state = 0;
     cudaStream_t st = S(s);
     const int N = *myDim_nod2D, Hn = *eDim_nod2D, E = *myDim_elem2D, G = *myDim_edge2D;
-    if (vlimit && *vlimit != 1) {
-        std::fprintf(stderr, "fesom2-accelerate: only vlimit == 1 is implemented (as in the reference)\n");
+    const int vl = vlimit ? *vlimit : 1;
+    if (vl < 1 || vl > 3) {
+        std::fprintf(stderr, "fesom2-accelerate: vlimit = %d (1, 2 or 3)\n", vl);
         return;
     }
     Plan *p = plan_for_handles(N, Hn, E, G, *nl, dev<int>(nlevels_elem2D), dev<int>(elem2D_nodes),
@@ -753,7 +767,7 @@ void fct_ale_pre_comm_acc_(int *alg_state, void **s, void **fct_ttf_max, void **
 
     wait_upload(H(ttf), st);
     bool ok = true;
-    if (g_fused.load()) {
+    if (g_fused.load() && vl == 1) {   // the fused phase implements vlimit 1; 2 and 3 run stage by stage
         // a1 on the halo rows keeps fct_ttf_max/min identical to the staged run there
         ok = ok && launch_stage(ST_A1, 1, A, M, nullptr, N, Hn, 1, st);
         wait_upload(H(fct_adf_v), st);
@@ -764,7 +778,7 @@ void fct_ale_pre_comm_acc_(int *alg_state, void **s, void **fct_ttf_max, void **
         if (ok) *alg_state = 1;
         ok = ok && launch_stage(ST_A2, 1, A, M, nullptr, 0, E, 1, st);
         if (ok) *alg_state = 2;
-        ok = ok && launch_stage(ST_A3, 1, A, M, nullptr, 0, N, 1, st);
+        ok = ok && launch_stage(vl == 1 ? ST_A3 : (vl == 2 ? ST_A3_VLIMIT2 : ST_A3_VLIMIT3), 1, A, M, nullptr, 0, N, 1, st);
         if (ok) *alg_state = 3;
         wait_upload(H(fct_adf_v), st);
         ok = ok && launch_stage(ST_B1V, 1, A, M, nullptr, 0, N, 1, st);

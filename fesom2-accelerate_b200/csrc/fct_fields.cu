@@ -23,12 +23,14 @@ static FieldMeta meta_of(int id)
 {
     switch (id) {
     case FCT_ADF_V:
+    case FCT_ADF_V2:
     case FCT_ADF_V_OUT: return {ROW_NODE, 0, true};
     case FCT_AREA:
     case FCT_AREA_INV: return {ROW_NODE, 0, false};
     case FCT_HNODE:
     case FCT_HNODE_NEW: return {ROW_NODE, 1, false};
     case FCT_ADF_H:
+    case FCT_ADF_H2:
     case FCT_ADF_H_OUT: return {ROW_EDGE, 1, true};
     case FCT_UV_RHS: return {ROW_ELEM, 1, true};
     default: return {ROW_NODE, 1, true};
@@ -72,6 +74,9 @@ static Arrays arrays_of(const Fields *f, int mode, double dt, double eps, double
     A.del_v = f->buf[FCT_DEL_V];
     A.del_h = f->buf[FCT_DEL_H];
     A.uv_rhs = reinterpret_cast<double2 *>(f->buf[FCT_UV_RHS]);
+    A.adf_v2 = f->buf[FCT_ADF_V2];
+    A.adf_h2 = f->buf[FCT_ADF_H2];
+    A.vlimit = 1;
     A.ts_node = f->ts_node;
     A.ts_nodev = f->ts_node;
     A.ts_edge = f->ts_edge;
@@ -222,6 +227,27 @@ void fct_ale_plan_pitch_(void **plan, int *pitch)
     *pitch = p ? p->pitch : 0;
 }
 
+static size_t field_doubles(const Fields *f, int id)
+{
+    const FieldMeta m = meta_of(id);
+    size_t n = field_rows(f, m.kind) * f->P * (m.per_tracer ? f->T : 1) * (id == FCT_UV_RHS ? 2 : 1);
+    if (f->packed) n = (m.kind == ROW_EDGE ? f->ts_edge : f->ts_node) * (m.per_tracer ? f->T : 1);
+    return n ? n : 1;
+}
+
+// buffers of the iterative branch (rejected flux parts), allocated at their first use
+static bool ensure_iter_buffers(Fields *f)
+{
+    for (int id : {(int)FCT_ADF_V2, (int)FCT_ADF_H2}) {
+        if (f->buf[id]) continue;
+        const size_t n = field_doubles(f, id);
+        if (!cuda_ok(cudaMalloc(&f->buf[id], n * sizeof(double)), "cudaMalloc(iter buffers)") ||
+            !cuda_ok(cudaMemset(f->buf[id], 0, n * sizeof(double)), "cudaMemset(iter buffers)"))
+            return false;
+    }
+    return true;
+}
+
 static void fields_create(void **fields, void **plan, int *ntracers, bool with_uv, bool packed, int *istat)
 {
     *fields = nullptr;
@@ -245,10 +271,8 @@ static void fields_create(void **fields, void **plan, int *ntracers, bool with_u
     bool ok = true;
     for (int id = 0; id < FCT_FIELD_COUNT && ok; ++id) {
         if (id == FCT_UV_RHS && (!with_uv || packed)) continue;
-        const FieldMeta m = meta_of(id);
-        size_t n = field_rows(f, m.kind) * f->P * (m.per_tracer ? f->T : 1) * (id == FCT_UV_RHS ? 2 : 1);
-        if (packed) n = (m.kind == ROW_EDGE ? f->ts_edge : f->ts_node) * (m.per_tracer ? f->T : 1);
-        n = n ? n : 1;
+        if (id == FCT_ADF_V2 || id == FCT_ADF_H2) continue;   // on demand: ensure_iter_buffers
+        const size_t n = field_doubles(f, id);
         ok = cuda_ok(cudaMalloc(&f->buf[id], n * sizeof(double)), "cudaMalloc(fields)") &&
              cuda_ok(cudaMemset(f->buf[id], 0, n * sizeof(double)), "cudaMemset(fields)");
     }
@@ -290,6 +314,7 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
 {
     *istat = 1;
     Fields *f = F_(fields);
+    if (f && (*field == FCT_ADF_V2 || *field == FCT_ADF_H2) && !f->packed && !ensure_iter_buffers(f)) return;
     if (!f || *field < 0 || *field >= FCT_FIELD_COUNT || !f->buf[*field] || !host) return;
     const FieldMeta m = meta_of(*field);
     const int t = m.per_tracer ? *tracer : 0;
@@ -393,8 +418,9 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     if (!f) return;
     const Plan *p = f->plan;
     const int st = *stage;
+    if (st < 0 || st > ST_LAST) return;
+    if (st >= ST_B3V_ITER && !f->packed && !ensure_iter_buffers(f)) return;
     const Arrays A = arrays_of(f, (st >= ST_PHASE_A && st < ST_B1H_ATOMIC) ? 1 : 0, *dt, *flux_eps, *bignumber);
-    if (st < 0 || st > ST_CH_ATOMIC) return;
     if (f->packed && !(st >= ST_PHASE_A_WARP && st <= 23)) {
         std::fprintf(stderr, "fesom2-accelerate: packed fields run the warp-item kernels only (stages 18-23)\n");
         return;
@@ -434,8 +460,8 @@ void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, rea
     int count = p->N;
     if (st == ST_A1) count = p->N + p->H;
     else if (st == ST_A2) count = p->E;
-    else if (st == ST_B3H || st == ST_B1H_ATOMIC || st == ST_CH_ATOMIC) count = p->G;
-    if (st == ST_A2 || st == ST_A3) {
+    else if (st == ST_B3H || st == ST_B1H_ATOMIC || st == ST_CH_ATOMIC || st == ST_B3H_ITER) count = p->G;
+    if (st == ST_A2 || st == ST_A3 || st == ST_A3_VLIMIT2 || st == ST_A3_VLIMIT3) {
         if (!f->buf[FCT_UV_RHS]) {
             std::fprintf(stderr, "fesom2-accelerate: stage %d needs fields created with UV_rhs\n", st);
             return;
@@ -512,6 +538,62 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
     if (!phase(ST_PHASE_B, 2)) return;
     if (!cuda_ok(cudaStreamWaitEvent(s, halo_event(h, 1), 0), "wait")) return;
     if (!phase(ST_PHASE_B, 1)) return;
+    *alg_state = 10;
+}
+
+void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimit, int *iter_yn, real_type *dt,
+                            real_type *flux_eps, real_type *bignumber, int *alg_state)
+{
+    *alg_state = 0;
+    Fields *f = F_(fields);
+    if (!f) return;
+    const Plan *p = f->plan;
+    cudaStream_t s = S_(stream);
+    Halo *h = (halo && *halo) ? static_cast<Halo *>(*halo) : nullptr;
+    if (h && !halo_valid(h)) return;
+    const int vl = *vlimit, N = p->N;
+    const bool iter = *iter_yn != 0;
+    if (vl < 1 || vl > 3) {
+        std::fprintf(stderr, "fesom2-accelerate: vlimit = %d (1, 2 or 3)\n", vl);
+        return;
+    }
+    if (f->packed || !f->buf[FCT_UV_RHS]) {
+        std::fprintf(stderr, "fesom2-accelerate: the general step runs the stage kernels: padded fields created with UV_rhs\n");
+        return;
+    }
+    if (iter && !ensure_iter_buffers(f)) return;
+    const Arrays A = arrays_of(f, 0, *dt, *flux_eps, *bignumber);
+    const int a3 = vl == 1 ? ST_A3 : (vl == 2 ? ST_A3_VLIMIT2 : ST_A3_VLIMIT3);
+    const int pre[6] = {ST_A1, ST_A2, a3, ST_B1V, ST_B1H, ST_B2};
+    const int cnt[6] = {N + p->H, p->E, N, N, N, N};
+    for (int i = 0; i < 6; ++i) {
+        if (!run_stage(f, A, pre[i], nullptr, 0, cnt[i], s)) return;
+        *alg_state = i + 1;
+    }
+    if (h && !halo_exchange(f, h, s)) return;
+    if (!iter) {
+        static const int post[4] = {ST_B3V, ST_B3H, ST_CV, ST_CH};
+        const int cnt2[4] = {N, p->G, N, N};
+        for (int i = 0; i < 4; ++i) {
+            if (!run_stage(f, A, post[i], nullptr, 0, cnt2[i], s)) return;
+            *alg_state = 7 + i;
+        }
+        return;
+    }
+    // docs/refactoring.md:226-290: limit, keep the rejected parts, update the low-order solution,
+    // hand the rejected parts to the next pass; fct_LO halo rows travel to the neighbours
+    if (!run_stage(f, A, ST_B3V_ITER, nullptr, 0, N, s)) return;
+    *alg_state = 7;
+    if (!run_stage(f, A, ST_B3H_ITER, nullptr, 0, p->G, s)) return;
+    *alg_state = 8;
+    if (!run_stage(f, A, ST_LO_UPDATE, nullptr, 0, N, s)) return;
+    *alg_state = 9;
+    if (!cuda_ok(cudaMemcpyAsync(f->buf[FCT_ADF_V], f->buf[FCT_ADF_V2], field_doubles(f, FCT_ADF_V) * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s), "fct_adf_v = fct_adf_v2") ||
+        !cuda_ok(cudaMemcpyAsync(f->buf[FCT_ADF_H], f->buf[FCT_ADF_H2], field_doubles(f, FCT_ADF_H) * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, s), "fct_adf_h = fct_adf_h2"))
+        return;
+    if (h && !halo_exchange_field(f, h, s, FCT_LO)) return;
     *alg_state = 10;
 }
 

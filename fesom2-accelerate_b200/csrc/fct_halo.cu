@@ -132,7 +132,7 @@ __global__ void k_halo_pack_columns(const double *__restrict__ plus, const doubl
     }
 }
 
-static bool halo_exchange_packed(Fields *f, Halo *h, cudaStream_t s)
+static bool halo_exchange_packed(Fields *f, Halo *h, cudaStream_t s, double *plus, double *minus, int narr)
 {
     const Plan *p = f->plan;
     const int T = f->T;
@@ -149,7 +149,6 @@ static bool halo_exchange_packed(Fields *f, Halo *h, cudaStream_t s)
         if (!cuda_ok(cudaMalloc(&h->sendbuf, std::max<size_t>(need, 1) * sizeof(double)), "cudaMalloc(halo)")) return false;
         h->sendbuf_doubles = need;
     }
-    double *plus = f->buf[FCT_PLUS], *minus = f->buf[FCT_MINUS];
     if (h->total_send > 0) {
         dim3 grid(h->total_send, T);
         k_halo_pack_columns<<<grid, 64, 0, s>>>(plus, minus, h->d_send_nodes, h->d_send_col, p->d_ncol, total, f->ts_node, h->sendbuf);
@@ -163,7 +162,7 @@ static bool halo_exchange_packed(Fields *f, Halo *h, cudaStream_t s)
         const size_t s0 = h->send_col[h->send_off[k]], sn = h->send_col[h->send_off[k] + h->send_cnt[k]] - s0;
         const size_t r0 = p->ncol[h->recv_first[k]], rn = p->ncol[h->recv_first[k] + h->recv_cnt[k]] - r0;
         for (int t = 0; t < T && ok; ++t) {
-            for (int a = 0; a < 2 && ok; ++a) {
+            for (int a = 0; a < narr && ok; ++a) {
                 if (sn > 0)
                     ok = nccl_ok(ncclSend(h->sendbuf + (size_t)(t * 2 + a) * total + s0, sn, ncclDouble, peer, h->comm, s), "ncclSend");
                 if (ok && rn > 0)
@@ -175,13 +174,14 @@ static bool halo_exchange_packed(Fields *f, Halo *h, cudaStream_t s)
     return ok;
 }
 
-bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
+// owned-boundary rows -> the neighbours' halo rows of `narr` (1 or 2) node arrays of f
+static bool halo_exchange_arrays(Fields *f, Halo *h, cudaStream_t s, double *plus, double *minus, int narr)
 {
     if (!halo_valid(h) || h->plan != f->plan) {
         std::fprintf(stderr, "fesom2-accelerate: halo does not belong to these fields\n");
         return false;
     }
-    if (f->packed) return halo_exchange_packed(f, h, s);
+    if (f->packed) return halo_exchange_packed(f, h, s, plus, minus, narr);
     const int P = f->P, T = f->T;
     const size_t need = (size_t)2 * T * h->total_send * P;
     if (need > h->sendbuf_doubles) {
@@ -191,7 +191,6 @@ bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
         if (!cuda_ok(cudaMalloc(&h->sendbuf, need * sizeof(double)), "cudaMalloc(halo)")) return false;
         h->sendbuf_doubles = need;
     }
-    double *plus = f->buf[FCT_PLUS], *minus = f->buf[FCT_MINUS];
     if (h->total_send > 0) {
         const int lx = P / 2;
         const int ny = 256 / lx > 0 ? 256 / lx : 1;
@@ -205,7 +204,7 @@ bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
     for (size_t k = 0; k < h->peers.size() && ok; ++k) {
         const int peer = h->peers[k];
         for (int t = 0; t < T && ok; ++t) {
-            for (int a = 0; a < 2 && ok; ++a) {
+            for (int a = 0; a < narr && ok; ++a) {
                 if (h->send_cnt[k] > 0)
                     ok = nccl_ok(ncclSend(h->sendbuf + ((size_t)(t * 2 + a) * h->total_send + h->send_off[k]) * P,
                                           (size_t)h->send_cnt[k] * P, ncclDouble, peer, h->comm, s), "ncclSend");
@@ -217,6 +216,17 @@ bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
     }
     ok = nccl_ok(ncclGroupEnd(), "ncclGroupEnd") && ok;
     return ok;
+}
+
+bool halo_exchange(Fields *f, Halo *h, cudaStream_t s)
+{
+    return halo_exchange_arrays(f, h, s, f->buf[FCT_PLUS], f->buf[FCT_MINUS], 2);
+}
+
+bool halo_exchange_field(Fields *f, Halo *h, cudaStream_t s, int field)
+{
+    double *a = f->buf[field];
+    return a && halo_exchange_arrays(f, h, s, a, a, 1);
 }
 
 }   // namespace fct
@@ -319,6 +329,21 @@ void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *ista
     if (!f || f->magic != FIELDS_MAGIC || !halo_valid(h)) return;
     cudaStream_t s = (stream && *stream) ? *static_cast<cudaStream_t *>(*stream) : (cudaStream_t)0;
     if (halo_exchange(f, h, s)) *istat = 0;
+}
+
+void fct_ale_halo_exchange_field_(void **fields, void **halo, void **stream, int *field, int *istat)
+{
+    Fields *f = fields ? static_cast<Fields *>(*fields) : nullptr;
+    Halo *h = halo ? static_cast<Halo *>(*halo) : nullptr;
+    *istat = 1;
+    if (!f || f->magic != FIELDS_MAGIC || !halo_valid(h)) return;
+    // node arrays of pitch nl-1 only (the rows the pack kernels move)
+    const int id = *field;
+    const bool node_L = id == FCT_TTF || id == FCT_LO || id == FCT_DEL_V || id == FCT_DEL_H || id == FCT_TTF_MAX ||
+                        id == FCT_TTF_MIN || id == FCT_PLUS || id == FCT_MINUS;
+    if (!node_L) return;
+    cudaStream_t s = (stream && *stream) ? *static_cast<cudaStream_t *>(*stream) : (cudaStream_t)0;
+    if (halo_exchange_field(f, h, s, id)) *istat = 0;
 }
 
 }   // extern "C"

@@ -11,7 +11,9 @@ enum Stage {
     ST_A1 = 0, ST_A2 = 1, ST_A3 = 2, ST_B1V = 3, ST_B1H = 4, ST_B2 = 5, ST_B3V = 6, ST_B3H = 7,
     ST_CV = 8, ST_CH = 9, ST_PHASE_A = 10, ST_PHASE_B = 11, ST_PHASE_A_TILE = 12, ST_PHASE_B_TILE = 13,
     ST_PHASE_A_WARP = 18, ST_PHASE_B_WARP = 19,
-    ST_B1H_ATOMIC = 24, ST_CH_ATOMIC = 25   // measured alternatives (fp64 atomics), never on the product path
+    ST_B1H_ATOMIC = 24, ST_CH_ATOMIC = 25,   // measured alternatives (fp64 atomics), never on the product path
+    // vlimit 2 / 3 and the iterative branch (docs/refactoring.md:113-148, :226-290)
+    ST_A3_VLIMIT2 = 26, ST_A3_VLIMIT3 = 27, ST_B3V_ITER = 28, ST_B3H_ITER = 29, ST_LO_UPDATE = 30, ST_LAST = 30
 };
 
 bool cuda_ok(cudaError_t e, const char *what);
@@ -30,7 +32,7 @@ Plan *create_plan_host(int N, int H, int E, int G, int nl, const int *nlev_n, co
                        const int *edges, const int *edge_tri);
 void destroy_plan(Plan *p);
 
-static const int FCT_FIELD_COUNT_INTERNAL = 17;   // == FCT_FIELD_COUNT of the public header
+static const int FCT_FIELD_COUNT_INTERNAL = 19;   // == FCT_FIELD_COUNT of the public header
 static const unsigned FIELDS_MAGIC = 0x464c4453u;
 static const unsigned HALO_MAGIC = 0x48414c4fu;
 static const unsigned PLAN_MAGIC = 0x504c414eu;
@@ -53,6 +55,8 @@ struct Fields {
 struct Halo;
 // pack + send/recv of fct_plus / fct_minus on stream s (all tracers of f)
 bool halo_exchange(Fields *f, Halo *h, cudaStream_t s);
+// the same for one per-tracer node array (fct_LO between two passes of the iterative branch, ttf, ...)
+bool halo_exchange_field(Fields *f, Halo *h, cudaStream_t s, int field);
 // streams / events used to overlap the exchange with interior work
 cudaStream_t halo_comm_stream(Halo *h);
 cudaEvent_t halo_event(Halo *h, int which);

@@ -35,6 +35,9 @@ struct Arrays {
     int pitchU;   // row pitch of UV_rhs (double2 units)
     int nl;
     double dt, eps, big;
+    // vlimit 2 / 3 and the iterative branch (docs/refactoring.md:113-148, :226-290)
+    int vlimit;
+    double *adf_v2, *adf_h2;   // rejected flux parts of b3 with iter_yn
 };
 
 struct MeshDev {
@@ -170,6 +173,38 @@ __global__ void k_a2(Arrays A, MeshDev M, const int *list, int first, int count)
     }
 }
 
+// cluster bounds of one node slot: max / min of UV_rhs over the ring elements (reference.cpp:362-378)
+template <int VEC>
+__device__ __forceinline__ void a3_ring_bounds(const Arrays &A, const MeshDev &M, int n, int z0, int nz,
+                                               double (&hi)[VEC], double (&lw)[VEC])
+{
+    const int *ring = M.nie + (size_t)n * M.nie_dim;
+    const int cnt = __ldg(M.nie_num + n);
+    const double2 *uvb = A.uv_rhs + blockIdx.y * A.ts_uv + z0;
+    {
+        const double2 *uv = uvb + (size_t)(__ldg(ring) - 1) * A.pitchU;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (z0 + v < nz) {
+                const double2 t = uv[v];
+                hi[v] = t.x;
+                lw[v] = t.y;
+            }
+        }
+    }
+    for (int k = 1; k < cnt; ++k) {
+        const double2 *uv = uvb + (size_t)(__ldg(ring + k) - 1) * A.pitchU;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (z0 + v < nz) {
+                const double2 t = uv[v];
+                hi[v] = pick_max(hi[v], t.x);
+                lw[v] = pick_min(lw[v], t.y);
+            }
+        }
+    }
+}
+
 // a3 -- reference.cpp:353-392 (bounds only; b1 vertical is its own kernel like kernels/fct_ale_b1_vertical.cu)
 // dynamic smem: NY * 2 * (LX*VEC + 2) doubles
 template <int VEC>
@@ -185,31 +220,7 @@ __global__ void k_a3(Arrays A, MeshDev M, const int *list, int first, int count)
     const bool act = it.z0 < nz;
     double hi[VEC], lw[VEC];
     if (act) {
-        const int *ring = M.nie + (size_t)n * M.nie_dim;
-        const int cnt = __ldg(M.nie_num + n);
-        const double2 *uvb = A.uv_rhs + blockIdx.y * A.ts_uv + it.z0;
-        {
-            const double2 *uv = uvb + (size_t)(__ldg(ring) - 1) * A.pitchU;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                if (it.z0 + v < nz) {
-                    const double2 t = uv[v];
-                    hi[v] = t.x;
-                    lw[v] = t.y;
-                }
-            }
-        }
-        for (int k = 1; k < cnt; ++k) {
-            const double2 *uv = uvb + (size_t)(__ldg(ring + k) - 1) * A.pitchU;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                if (it.z0 + v < nz) {
-                    const double2 t = uv[v];
-                    hi[v] = pick_max(hi[v], t.x);
-                    lw[v] = pick_min(lw[v], t.y);
-                }
-            }
-        }
+        a3_ring_bounds<VEC>(A, M, n, it.z0, nz, hi, lw);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             if (it.z0 + v < nz) {
@@ -231,6 +242,58 @@ __global__ void k_a3(Arrays A, MeshDev M, const int *list, int first, int count)
             if (z > 0 && z < nz - 1) {
                 bm = pick_max(pick_max(tvmax[z - 1], bm), tvmax[z + 1]);
                 bn = pick_min(pick_min(tvmin[z - 1], bn), tvmin[z + 1]);
+            }
+            omax[v] = bm - l[v];
+            omin[v] = bn - l[v];
+        }
+    }
+    const int cnt = min(VEC, nz - it.z0);
+    stv<VEC>(A.ttf_max + off, omax, cnt);
+    stv<VEC>(A.ttf_min + off, omin, cnt);
+}
+
+// a3 with vlimit == 2 (docs/refactoring.md:113-129) or 3 (md:131-148): the horizontal cluster bound
+// of a level is widened (2) or narrowed (3) by the node's own a1 maxima of levels z-1..z+1 -- the
+// listing takes maxval AND minval from fct_ttf_max (md:120-121, :139-140), restated as written.
+// No executable form exists in the reference (reference.cpp:51-96 stubs, fct_ale_a3.py:152-155 pass).
+// dynamic smem as k_a3 (one array used): the own a1 maxima, read before any level is overwritten
+template <int VEC>
+__global__ void k_a3_vlimit(Arrays A, MeshDev M, const int *list, int first, int count)
+{
+    extern __shared__ double sm[];
+    const int W = blockDim.x * VEC + 2;
+    double *amax = sm + (size_t)threadIdx.y * 2 * W + 1;
+    const Item it = my_item(list, first, count, VEC);
+    const int n = it.idx;
+    const int nz = (n >= 0) ? __ldg(M.nlev_n + n) - 1 : 0;
+    const bool act = it.z0 < nz;
+    const size_t off = act ? blockIdx.y * A.ts_node + (size_t)n * A.pitchL + it.z0 : 0;
+    double hi[VEC], lw[VEC];
+    if (act) {
+        a3_ring_bounds<VEC>(A, M, n, it.z0, nz, hi, lw);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (it.z0 + v < nz) amax[it.z0 + v] = A.ttf_max[off + v];
+    }
+    __syncthreads();
+    if (!act) return;
+    double l[VEC], omax[VEC], omin[VEC];
+    ldv_ro<VEC>(A.lo + off, l);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int z = it.z0 + v;
+        if (z < nz) {
+            double bm = hi[v], bn = lw[v];
+            if (z > 0 && z < nz - 1) {
+                const double vmax = pick_max(pick_max(amax[z - 1], amax[z]), amax[z + 1]);
+                const double vmin = pick_min(pick_min(amax[z - 1], amax[z]), amax[z + 1]);
+                if (A.vlimit == 2) {
+                    bm = pick_max(bm, vmax);
+                    bn = pick_min(bn, vmin);
+                } else {
+                    bm = pick_min(bm, vmax);
+                    bn = pick_max(bn, vmin);
+                }
             }
             omax[v] = bm - l[v];
             omin[v] = bn - l[v];
@@ -352,7 +415,7 @@ __global__ void k_b2(Arrays A, MeshDev M, const int *list, int first, int count)
 
 // limited vertical flux at level z of a column (docs/refactoring.md:205-231): raw flux f,
 // own-column factors p/m (rows of fct_plus / fct_minus)
-__device__ __forceinline__ double b3v_point(double f, int z, const double *p, const double *m)
+__device__ __forceinline__ double b3v_factor(double f, int z, const double *p, const double *m)
 {
     double ae = 1.;
     if (z == 0) {
@@ -365,7 +428,11 @@ __device__ __forceinline__ double b3v_point(double f, int z, const double *p, co
         ae = pick_min(ae, p[z - 1]);
         ae = pick_min(ae, m[z]);
     }
-    return ae * f;
+    return ae;
+}
+__device__ __forceinline__ double b3v_point(double f, int z, const double *p, const double *m)
+{
+    return b3v_factor(f, z, p, m) * f;
 }
 
 // b3 vertical -- docs/refactoring.md:205-233 (in place; each level depends on its own raw flux only)
@@ -389,7 +456,7 @@ __global__ void k_b3v(Arrays A, MeshDev M, const int *list, int first, int count
 
 // limiter factor times flux of one edge level (docs/refactoring.md:246-261).
 // p1/m1 belong to edges[2g], p2/m2 to edges[2g+1].
-__device__ __forceinline__ double b3h_point(double h, double p1, double m1, double p2, double m2)
+__device__ __forceinline__ double b3h_factor(double h, double p1, double m1, double p2, double m2)
 {
     double ae = 1.;
     if (h >= 0.) {
@@ -399,7 +466,11 @@ __device__ __forceinline__ double b3h_point(double h, double p1, double m1, doub
         ae = pick_min(ae, m1);
         ae = pick_min(ae, p2);
     }
-    return ae * h;
+    return ae;
+}
+__device__ __forceinline__ double b3h_point(double h, double p1, double m1, double p2, double m2)
+{
+    return b3h_factor(h, p1, m1, p2, m2) * h;
 }
 
 __device__ __forceinline__ int edge_depth_dev(const MeshDev &M, int g)
@@ -497,6 +568,115 @@ __global__ void k_ch(Arrays A, MeshDev M, const int *list, int first, int count)
         }
     }
     stv<VEC>(A.del_h + off, d, min(VEC, nz - it.z0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// The iterative branch (iter_yn, docs/refactoring.md:226-290): b3 also
+// keeps the rejected part of every flux, the limited fluxes update the low-order solution, and the
+// rejected parts become the antidiffusive fluxes of the next pass.  No executable form exists in
+// the reference; operation order is the listing's.
+// ------------------------------------------------------------------------------------------------
+
+// b3 vertical with iter_yn -- md:205-233: adf_v2 = (1-ae)*flux below the surface level (md:228-230)
+template <int VEC>
+__global__ void k_b3v_iter(Arrays A, MeshDev M, const int *list, int first, int count)
+{
+    const Item it = my_item(list, first, count, VEC);
+    if (it.idx < 0) return;
+    const int nz = __ldg(M.nlev_n + it.idx) - 1;
+    if (it.z0 >= nz) return;
+    const size_t vo = blockIdx.y * A.ts_nodev + (size_t)it.idx * A.pitchV;
+    double *vrow = A.adf_v + vo, *v2row = A.adf_v2 + vo;
+    const size_t off = blockIdx.y * A.ts_node + (size_t)it.idx * A.pitchL;
+    const double *p = A.plus + off, *m = A.minus + off;
+    double f[VEC];
+    ldv<VEC>(vrow + it.z0, f);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const int z = it.z0 + v;
+        if (z < nz) {
+            const double ae = b3v_factor(f[v], z, p, m);
+            if (z > 0) v2row[z] = (1.0 - ae) * f[v];
+            f[v] = ae * f[v];
+        }
+    }
+    stv<VEC>(vrow + it.z0, f, min(VEC, nz - it.z0));
+}
+
+// b3 horizontal with iter_yn -- md:238-263
+template <int VEC>
+__global__ void k_b3h_iter(Arrays A, MeshDev M, const int *list, int first, int count)
+{
+    const Item it = my_item(list, first, count, VEC);
+    if (it.idx < 0) return;
+    const int g = it.idx;
+    const int dg = edge_depth_dev(M, g);
+    if (it.z0 >= dg) return;
+    const size_t tb = blockIdx.y * A.ts_node + it.z0;
+    const size_t r1 = tb + (size_t)(__ldg(M.edges + 2 * g) - 1) * A.pitchL;
+    const size_t r2 = tb + (size_t)(__ldg(M.edges + 2 * g + 1) - 1) * A.pitchL;
+    const size_t ho = blockIdx.y * A.ts_edge + (size_t)g * A.pitchH + it.z0;
+    double h[VEC], h2[VEC], p1[VEC], m1[VEC], p2[VEC], m2[VEC];
+    ldv<VEC>(A.adf_h_in + ho, h);
+    ldv_ro<VEC>(A.plus + r1, p1);
+    ldv_ro<VEC>(A.minus + r1, m1);
+    ldv_ro<VEC>(A.plus + r2, p2);
+    ldv_ro<VEC>(A.minus + r2, m2);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        if (it.z0 + v < dg) {
+            const double ae = b3h_factor(h[v], p1[v], m1[v], p2[v], m2[v]);
+            h2[v] = (1.0 - ae) * h[v];
+            h[v] = ae * h[v];
+        }
+    }
+    const int cnt = min(VEC, dg - it.z0);
+    stv<VEC>(A.adf_h_out + ho, h, cnt);
+    stv<VEC>(A.adf_h2 + ho, h2, cnt);
+}
+
+// "c. Update the LO" -- md:265-287, node-centric: the vertical term first, then the node's edges in
+// ascending edge id (the order in which the listing's two loops reach this node); x*dt/area/hnode_new
+// is evaluated left to right as written.  Owned nodes only: halo rows of fct_LO are the caller's
+// exchange before the next pass, as in the Fortran.
+template <int VEC>
+__global__ void k_lo_update(Arrays A, MeshDev M, const int *list, int first, int count)
+{
+    const Item it = my_item(list, first, count, VEC);
+    if (it.idx < 0) return;
+    const int n = it.idx;
+    const int nz = __ldg(M.nlev_n + n) - 1;
+    if (it.z0 >= nz) return;
+    const size_t off = blockIdx.y * A.ts_node + (size_t)n * A.pitchL + it.z0;
+    const double *vrow = A.adf_v + blockIdx.y * A.ts_nodev + (size_t)n * A.pitchV;
+    double *lo = const_cast<double *>(A.lo);
+    double l[VEC], ar[VEC], hw[VEC], f[VEC + 1];
+    ldv<VEC>(lo + off, l);
+    ldv_ro<VEC>(A.area + (size_t)n * A.pitchV + it.z0, ar);
+    ldv_ro<VEC>(A.hnode_new + (size_t)n * A.pitchL + it.z0, hw);
+#pragma unroll
+    for (int v = 0; v <= VEC; ++v) f[v] = (it.z0 + v <= nz) ? vrow[it.z0 + v] : 0.0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) l[v] = l[v] + (f[v] - f[v + 1]) * A.dt / ar[v] / hw[v];
+    const double *hb = A.adf_h_out + blockIdx.y * A.ts_edge + it.z0;
+    const int b = __ldg(M.edg_off + n), e = __ldg(M.edg_off + n + 1);
+    for (int k = b; k < e; ++k) {
+        const int4 en = __ldg(M.edg + k);
+        const int dg = FCT_META_DEPTH(en.z);
+        if (it.z0 < dg) {
+            double h[VEC];
+            ldv<VEC>(hb + (size_t)en.x * A.pitchH, h);
+            const bool second = FCT_META_SECOND(en.z);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (it.z0 + v < dg) {
+                    const double x = h[v] * A.dt / ar[v] / hw[v];
+                    l[v] = second ? l[v] - x : l[v] + x;
+                }
+            }
+        }
+    }
+    stv<VEC>(lo + off, l, min(VEC, nz - it.z0));
 }
 
 // ------------------------------------------------------------------------------------------------

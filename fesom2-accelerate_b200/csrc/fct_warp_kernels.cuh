@@ -54,6 +54,8 @@ struct WarpTilesDev {
     int ntiles;
     int smem_bytes;             // shared memory of one stage (max over tiles)
     int diag;                   // timing experiments only (wrong results): 1 skip the edge-row copies, 2 skip all row copies
+    int opt;                    // scheduling options (results unaffected): 1 producers wait suspended in hardware
+                                // instead of polling, 2 consumers issue a tile's first loads before waiting for its rows
 };
 
 // warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A WT_CONVERTERS a1 converters, then NWC
@@ -129,8 +131,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 // producer-side wait: producers are idle most of the time; probe, then sleep between probes so that
 // they leave the issue slots to the consumers (costs a fraction of a microsecond per hand-over)
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, bool suspended = false)
 {
+    if (suspended) {
+        mbar_wait(bar, parity);
+        return;
+    }
     uint32_t done = 0;
     for (;;) {
         asm volatile(
@@ -654,7 +660,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 // the stage is still busy: have the blob wait in L2
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(T.blob + b0), "r"((b1 - b0) * 16u) : "memory");
             }
-            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
             if (v >= total) {
                 if (lane == 0) {
                     tile_of[s] = -1;
@@ -682,7 +688,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         // ---- copy issuers: one bulk copy per staged row, the list shared by NPW warps ----
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
-            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1);
+            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt & 1);
             if (tile_of[s] < 0) break;
             const int tr = tracer_of[s];
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
@@ -707,10 +713,10 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         const int cl = (warp - NPW - 1) * 32 + lane;   // lane among the converter warps
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
-            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1);
+            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt & 1);
             if (tile_of[s] < 0) break;
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
-            mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1);
+            mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1, T.opt & 1);
             double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
             const int n16 = V.rows_bytes >> 4;
 #pragma unroll 4
@@ -735,15 +741,19 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             mbar_wait(b_blob(s), (it / NSTAGE) & 1);
             if (tile_of[s] < 0) break;
             const int tr = tracer_of[s];
-            mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            const bool first_loads_ahead = T.opt & 2;
+            if (!first_loads_ahead) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             const size_t tn = tr * A.ts_node;
             const double *g_v = A.adf_v + tr * A.ts_nodev;
             // one item ahead: lane 0 draws the next index at the top of an item; the item broadcasts
-            // it and loads the successor's first-needed values before its own edge loop
+            // it and loads the successor's first-needed values before its own edge loop.  The first
+            // item of a tile needs the blob only (schedule + node headers): its loads travel while the
+            // warp waits for the tile's rows
             int wi = __shfl_sync(0xffffffffu, draw(s), 0);
             WtEarly E;
             if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v, tn);
+            if (first_loads_ahead) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             while (wi < V.n_witems) {
                 WtEarly En;
                 int wn = 0;

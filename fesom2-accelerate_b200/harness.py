@@ -303,6 +303,23 @@ class DeviceFields:
             self.stream.sync()
         return st.value
 
+    def step_general(self, f: Fields, halo: Optional[HaloLink] = None, sync: bool = True) -> int:
+        """The subroutine with its vlimit (f.vlimit) and iter_yn (f.iter_yn) branches, stage kernels."""
+        st = C.c_int()
+        hp = C.byref(halo.h) if halo is not None else None
+        self.lib.fct_ale_step_general_(C.byref(self.h), hp, self.stream.ref, ci(f.vlimit), ci(1 if f.iter_yn else 0),
+                                       cd(f.dt), cd(f.flux_eps), cd(f.bignumber), C.byref(st))
+        if sync:
+            self.stream.sync()
+        return st.value
+
+    def exchange_field(self, halo: HaloLink, name: str):
+        st = C.c_int()
+        self.lib.fct_ale_halo_exchange_field_(C.byref(self.h), C.byref(halo.h), self.stream.ref,
+                                              ci(abi.FIELD_IDS[name]), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError(f"halo exchange of {name} failed")
+
     # the arrays that change every tracer step (hnode / hnode_new move with the ALE surface) and the
     # results FESOM2 consumes after fct_ale (the advective tendencies, docs/refactoring.md:292-314)
     STEP_INPUTS = ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "hnode", "hnode_new", "del_ttf_advvert",

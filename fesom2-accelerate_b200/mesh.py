@@ -102,6 +102,10 @@ class Fields:
     flux_eps: float = 1e-16
     bignumber: float = 1e3
     vlimit: int = 1
+    # iterative branch (docs/refactoring.md:226-290): rejected flux parts, inputs of the next pass
+    iter_yn: bool = False
+    fct_adf_v2: Optional[np.ndarray] = None
+    fct_adf_h2: Optional[np.ndarray] = None
 
     def copy(self) -> "Fields":
         kw = {}

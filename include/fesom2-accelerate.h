@@ -226,7 +226,10 @@ enum fct_field_id {
     FCT_TTF = 0, FCT_LO = 1, FCT_ADF_V = 2, FCT_ADF_H = 3, FCT_AREA = 4, FCT_AREA_INV = 5,
     FCT_HNODE = 6, FCT_HNODE_NEW = 7, FCT_DEL_V = 8, FCT_DEL_H = 9, FCT_TTF_MAX = 10,
     FCT_TTF_MIN = 11, FCT_PLUS = 12, FCT_MINUS = 13, FCT_UV_RHS = 14, FCT_ADF_H_OUT = 15,
-    FCT_ADF_V_OUT = 16, FCT_FIELD_COUNT = 17
+    FCT_ADF_V_OUT = 16,
+    /* rejected flux parts of the iterative branch (docs/refactoring.md:228-230, :258-260), padded
+     * fields only, allocated at first use */
+    FCT_ADF_V2 = 17, FCT_ADF_H2 = 18, FCT_FIELD_COUNT = 19
 };
 /* dense host array (the Fortran layout above) <-> padded device rows of tracer *tracer
  * (mesh-static fields area / area_inv / hnode / hnode_new ignore *tracer).  Asynchronous on
@@ -259,13 +262,23 @@ void fct_ale_field_link_bytes_(void **fields, int *field, real_type *host, int *
  * success. */
 void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_type *dt,
                    real_type *flux_eps, real_type *bignumber, int *alg_state);
+/* The whole subroutine of docs/refactoring.md:13-315 with the branches the reference never made
+ * executable (src/reference.cpp:51-96 are stubs): *vlimit 1, 2 or 3
+ * (md:77-148) and *iter_yn (md:226-290: b3 keeps the rejected part of every flux in FCT_ADF_V2 /
+ * FCT_ADF_H2, the limited fluxes update fct_LO, then fct_adf_* = fct_adf_*2 and -- with a halo --
+ * the fct_LO halo rows are exchanged for the next pass).  Stage kernels on padded fields created
+ * with UV_rhs, in place like mode 0 of fct_ale_step_; *alg_state = 10 on success. */
+void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimit, int *iter_yn, real_type *dt,
+                            real_type *flux_eps, real_type *bignumber, int *alg_state);
 /* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,
  * 6 b3v, 7 b3h, 8 c_v, 9 c_h; 10 fused phase A, 11 fused phase B; 12 / 13 the tile-staged
  * fused phases (14-17: their boundary / interior subsets); 18 / 19 the warp-item fused phases
  * (20 / 21: phase A on the boundary / interior tiles, 22 / 23: phase B);
  * 24 / 25: b1h / c_h as the reference's edge-centric fp64 atomicAdd scatter
  * (kernels/fct_ale_b1_horizontal.cu:24-27, fct_ale_c_horizontal.cu:25-26) -- a measured
- * alternative only: not bit-reproducible, never launched by fct_ale_step_ or the *_acc_ calls */
+ * alternative only: not bit-reproducible, never launched by fct_ale_step_ or the *_acc_ calls;
+ * 26 / 27: a3 with vlimit 2 / 3; 28 / 29: b3 vertical / horizontal with iter_yn; 30: the low-order
+ * update of the iterative branch (docs/refactoring.md:265-287) */
 void fct_ale_stage_(void **fields, void **stream, int *stage, real_type *dt, real_type *flux_eps,
                     real_type *bignumber, int *istat);
 
@@ -284,6 +297,9 @@ void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int 
 void fct_ale_halo_destroy_(void **halo, int *istat);
 /* the exchange alone (tests, timing) */
 void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *istat);
+/* exchange_nod of ONE per-tracer node array of width nl-1 (*field: FCT_LO between two passes of
+ * the iterative branch, FCT_TTF, ...): owned-boundary rows -> the neighbours' halo rows */
+void fct_ale_halo_exchange_field_(void **fields, void **halo, void **stream, int *field, int *istat);
 
 #ifdef __cplusplus
 }

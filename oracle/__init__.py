@@ -149,6 +149,58 @@ def fct_ale(m, f, exchange=None):
     post_comm(m, f)
 
 
+# ------------------------------------------------------------------ vlimit 2 / 3 and iter_yn
+# SURVEY.md section 8(f) row 2.  PARITY UNPINNED: the reference holds no executable form of these
+# branches (reference.cpp:51-96 TODO stubs, kernels/fct_ale_a3.py:152-155 `pass`); the restatement
+# follows docs/refactoring.md:113-148 and :226-290 line by line.
+def a3_vlimit(m, f):
+    if f.vlimit == 1:
+        return a3(m, f)
+    scratch = np.empty(2 * m.L)
+    lib().oracle_a3_vlimit(C.c_int(f.vlimit), C.c_int(m.myDim_nod2D), _i(m.nlevels_nod2D), C.c_int(m.nl),
+                           _d(f.fct_ttf_max), _d(f.fct_ttf_min), _d(f.fct_LO), _d(f.UV_rhs),
+                           _i(m.nod_in_elem2D), _i(m.nod_in_elem2D_num), C.c_int(m.nod_in_elem2D_dim),
+                           _d(scratch))
+
+
+def b3_vertical_iter(m, f):
+    lib().oracle_b3_vertical_iter(C.c_int(m.myDim_nod2D), _i(m.nlevels_nod2D), C.c_int(m.nl),
+                                  _d(f.fct_adf_v), _d(f.fct_adf_v2), _d(f.fct_plus), _d(f.fct_minus))
+
+
+def b3_horizontal_iter(m, f):
+    lib().oracle_b3_horizontal_iter(C.c_int(m.myDim_edge2D), C.c_int(m.nl), _i(m.nlevels_elem),
+                                    _i(m.edges), _i(m.edge_tri), _d(f.fct_adf_h), _d(f.fct_adf_h2),
+                                    _d(f.fct_plus), _d(f.fct_minus))
+
+
+def lo_update(m, f):
+    lib().oracle_lo_update(C.c_int(m.myDim_nod2D), C.c_int(m.myDim_edge2D), C.c_int(m.nl),
+                           _i(m.nlevels_nod2D), _i(m.nlevels_elem), _i(m.edges), _i(m.edge_tri),
+                           _d(f.fct_LO), _d(f.fct_adf_v), _d(f.fct_adf_h), _d(f.area), _d(f.hnode_new),
+                           C.c_double(f.dt))
+
+
+def fct_ale_general(m, f, exchange=None):
+    """The whole subroutine of docs/refactoring.md:13-315 with its vlimit and iter_yn branches.
+    iter_yn: ends after the low-order update with fct_adf_* = fct_adf_*2 (md:288-290)."""
+    a1(m, f)
+    a2(m, f)
+    a3_vlimit(m, f)
+    b1_vertical(m, f)
+    b1_horizontal(m, f)
+    b2(m, f)
+    if exchange is not None:
+        exchange(f)
+    if not f.iter_yn:
+        return post_comm(m, f)
+    b3_vertical_iter(m, f)
+    b3_horizontal_iter(m, f)
+    lo_update(m, f)
+    f.fct_adf_h[...] = f.fct_adf_h2
+    f.fct_adf_v[...] = f.fct_adf_v2
+
+
 # ------------------------------------------------------------------ the reference's own code
 def _ci(v):
     return C.byref(C.c_int(v))

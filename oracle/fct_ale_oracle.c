@@ -292,3 +292,137 @@ void oracle_post_comm(int my_nod, int my_edge, int nl, const int *nlev_nod, cons
     oracle_c_vertical(my_nod, nlev_nod, nl, del_v, ttf, hnode, lo, hnode_new, adf_v, area, dt);
     oracle_c_horizontal(my_edge, nl, nlev_elem, edges, edge_tri, adf_h, area, del_h, dt);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * the branches of the Fortran listing the reference never made
+ * executable (src/reference.cpp:51-96 are TODO stubs, kernels/fct_ale_a3.py:152-155 is `pass`).
+ * PARITY UNPINNED: no golden vector, test or runnable reference code exists for them; these
+ * functions follow docs/refactoring.md line by line, quirks included.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* a3 with vlimit == 2 (docs/refactoring.md:113-129) or vlimit == 3 (md:131-148).  On entry
+ * ttf_max / ttf_min hold the a1 bounds.  The listing takes BOTH the maxval and the minval of the
+ * vertical neighbourhood from fct_ttf_max (md:120-121, md:139-140); restated as written.
+ * scratch: 2*(nl-1) doubles. */
+void oracle_a3_vlimit(int vlimit, int n_nodes, const int *nlev_nod, int nl, double *ttf_max,
+                      double *ttf_min, const double *lo, const double *uv_rhs, const int *nod_in_elem,
+                      const int *nod_in_elem_num, int ring_dim, double *scratch)
+{
+    const size_t L = (size_t)nl - 1;
+    double *tv_max = scratch, *tv_min = scratch + L;
+    for (int n = 0; n < n_nodes; ++n) {
+        const int nz = nlev_nod[n] - 1;
+        const int *ring = nod_in_elem + (size_t)n * ring_dim;
+        const int cnt = nod_in_elem_num[n];
+        const double *uv = uv_rhs + (size_t)(ring[0] - 1) * L * 2;
+        for (int z = 0; z < nz; ++z) {
+            tv_max[z] = uv[2 * z];
+            tv_min[z] = uv[2 * z + 1];
+        }
+        for (int k = 1; k < cnt; ++k) {
+            uv = uv_rhs + (size_t)(ring[k] - 1) * L * 2;
+            for (int z = 0; z < nz; ++z) {
+                tv_max[z] = pick_max(tv_max[z], uv[2 * z]);
+                tv_min[z] = pick_min(tv_min[z], uv[2 * z + 1]);
+            }
+        }
+        double *hi = ttf_max + n * L, *lw = ttf_min + n * L;
+        for (int z = 1; z < nz - 1; ++z) {   /* nz = 2 .. nlevels_nod2D(n)-2, 1-based */
+            const double vmax = pick_max(pick_max(hi[z - 1], hi[z]), hi[z + 1]);
+            const double vmin = pick_min(pick_min(hi[z - 1], hi[z]), hi[z + 1]);
+            if (vlimit == 2) {
+                tv_max[z] = pick_max(tv_max[z], vmax);
+                tv_min[z] = pick_min(tv_min[z], vmin);
+            } else {
+                tv_max[z] = pick_min(tv_max[z], vmax);
+                tv_min[z] = pick_max(tv_min[z], vmin);
+            }
+        }
+        const double *l = lo + n * L;
+        for (int z = 0; z < nz; ++z) {
+            hi[z] = tv_max[z] - l[z];
+            lw[z] = tv_min[z] - l[z];
+        }
+    }
+}
+
+/* b3 vertical with iter_yn (md:205-233): the rejected part of every flux below the surface goes
+ * to adf_v2 (md:228-230; the surface level nz = 1 has no such statement, adf_v2 keeps its value). */
+void oracle_b3_vertical_iter(int n_nodes, const int *nlev_nod, int nl, double *adf_v, double *adf_v2,
+                             const double *plus, const double *minus)
+{
+    const size_t L = (size_t)nl - 1;
+    for (int n = 0; n < n_nodes; ++n) {
+        double *v = adf_v + (size_t)n * nl, *v2 = adf_v2 + (size_t)n * nl;
+        const double *p = plus + n * L, *m = minus + n * L;
+        double ae = 1.;
+        if (v[0] >= 0.) ae = pick_min(ae, p[0]);
+        else ae = pick_min(ae, m[0]);
+        v[0] = ae * v[0];
+        const int nz = nlev_nod[n] - 1;
+        for (int z = 1; z < nz; ++z) {
+            ae = 1.;
+            if (v[z] >= 0.) {
+                ae = pick_min(ae, m[z - 1]);
+                ae = pick_min(ae, p[z]);
+            } else {
+                ae = pick_min(ae, p[z - 1]);
+                ae = pick_min(ae, m[z]);
+            }
+            v2[z] = (1.0 - ae) * v[z];
+            v[z] = ae * v[z];
+        }
+    }
+}
+
+/* b3 horizontal with iter_yn (md:238-263) */
+void oracle_b3_horizontal_iter(int n_edges, int nl, const int *nlev_elem, const int *edges,
+                               const int *edge_tri, double *adf_h, double *adf_h2, const double *plus,
+                               const double *minus)
+{
+    const size_t L = (size_t)nl - 1;
+    for (int g = 0; g < n_edges; ++g) {
+        const size_t a = (size_t)(edges[2 * g] - 1) * L, b = (size_t)(edges[2 * g + 1] - 1) * L;
+        double *h = adf_h + (size_t)g * L, *h2 = adf_h2 + (size_t)g * L;
+        const int nz = edge_depth(edge_tri, nlev_elem, g);
+        for (int z = 0; z < nz; ++z) {
+            double ae = 1.;
+            if (h[z] >= 0.) {
+                ae = pick_min(ae, plus[a + z]);
+                ae = pick_min(ae, minus[b + z]);
+            } else {
+                ae = pick_min(ae, minus[a + z]);
+                ae = pick_min(ae, plus[b + z]);
+            }
+            h2[z] = (1.0 - ae) * h[z];
+            h[z] = ae * h[z];
+        }
+    }
+}
+
+/* "c. Update the LO" of the iterative branch (md:265-287), operation order of the listing:
+ * x*dt/area/hnode_new = ((x*dt)/area)/hnode_new.  Every end node of a local edge is updated,
+ * halo nodes included, as the edge loop of the listing does. */
+void oracle_lo_update(int n_nodes, int n_edges, int nl, const int *nlev_nod, const int *nlev_elem,
+                      const int *edges, const int *edge_tri, double *lo, const double *adf_v,
+                      const double *adf_h, const double *area, const double *hnode_new, double dt)
+{
+    const size_t L = (size_t)nl - 1;
+    for (int n = 0; n < n_nodes; ++n) {
+        const double *v = adf_v + (size_t)n * nl, *ar = area + (size_t)n * nl;
+        const int nz = nlev_nod[n] - 1;
+        for (int z = 0; z < nz; ++z) {
+            const size_t i = n * L + z;
+            lo[i] = lo[i] + (v[z] - v[z + 1]) * dt / ar[z] / hnode_new[i];
+        }
+    }
+    for (int g = 0; g < n_edges; ++g) {
+        const size_t n1 = (size_t)(edges[2 * g] - 1), n2 = (size_t)(edges[2 * g + 1] - 1);
+        const double *h = adf_h + (size_t)g * L;
+        const int nz = edge_depth(edge_tri, nlev_elem, g);
+        for (int z = 0; z < nz; ++z) {
+            lo[n1 * L + z] = lo[n1 * L + z] + h[z] * dt / area[n1 * nl + z] / hnode_new[n1 * L + z];
+            lo[n2 * L + z] = lo[n2 * L + z] - h[z] * dt / area[n2 * nl + z] / hnode_new[n2 * L + z];
+        }
+    }
+}

@@ -250,6 +250,78 @@ def test_atomic_alternatives(mesh_mod, harness, oracle_mod):
     plan.free()
 
 
+def general_case(mesh_mod, name, vlimit, iter_yn, seed=11):
+    m, f = cases(mesh_mod, name)
+    f.vlimit, f.iter_yn = vlimit, iter_yn
+    if iter_yn:
+        rng = np.random.default_rng(seed)      # adf_*2 cells the listing never writes keep their values
+        f.fct_adf_v2 = rng.standard_normal(f.fct_adf_v.shape)
+        f.fct_adf_h2 = rng.standard_normal(f.fct_adf_h.shape)
+    return m, f
+
+
+@pytest.mark.parametrize("name", ["tiny", "pi", "deep", "adversarial"])
+@pytest.mark.parametrize("vlimit,iter_yn", [(2, False), (3, False), (1, True), (3, True)])
+def test_vlimit_and_iterative_branches(mesh_mod, harness, oracle_mod, name, vlimit, iter_yn):
+    """vlimit 2 / 3 (docs/refactoring.md:113-148) and iter_yn
+    (md:226-290) against the restatement of the listing (parity unpinned: the reference has no
+    executable form of these branches)."""
+    m, f = general_case(mesh_mod, name, vlimit, iter_yn)
+    want = f.copy()
+    oracle_mod.fct_ale_general(m, want)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(f)
+    if iter_yn:
+        df.upload_field("fct_adf_v2", f.fct_adf_v2)
+        df.upload_field("fct_adf_h2", f.fct_adf_h2)
+    assert df.step_general(f) == 10
+    names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz",
+             "fct_adf_v", "fct_adf_h", "fct_LO", "UV_rhs"] + (["fct_adf_v2", "fct_adf_h2"] if iter_yn else [])
+    got = df.download(f, names=names)
+    for k in names:
+        assert bits_equal(getattr(got, k), getattr(want, k)), f"{k}: {rel_err(getattr(got, k), getattr(want, k), 1e-30):.3e}"
+    df.free()
+    plan.free()
+
+
+def test_iterative_passes_converge_to_the_plain_limiter_inputs(mesh_mod, harness, oracle_mod):
+    """Two passes of the iterative branch followed by the closing non-iterative call (the way
+    FESOM2 drives fct_ale with iter_yn), device against oracle."""
+    m, f = general_case(mesh_mod, "pi", 1, True)
+    want = f.copy()
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(f)
+    df.upload_field("fct_adf_v2", f.fct_adf_v2)
+    df.upload_field("fct_adf_h2", f.fct_adf_h2)
+    for it in (True, True, False):
+        want.iter_yn = f.iter_yn = it
+        oracle_mod.fct_ale_general(m, want)
+        assert df.step_general(f) == 10
+    names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz",
+             "fct_adf_v", "fct_adf_h", "fct_LO"]
+    got = df.download(f, names=names)
+    for k in names:
+        assert bits_equal(getattr(got, k), getattr(want, k)), k
+    df.free()
+    plan.free()
+
+
+def test_handle_abi_vlimit(mesh_mod, harness, abi, oracle_mod):
+    """fct_ale_pre_comm_acc_ honours its vlimit argument (2 and 3 run the stage kernels)."""
+    for vlimit in (2, 3):
+        m, f = general_case(mesh_mod, "pi", vlimit, False)
+        want = f.copy()
+        oracle_mod.fct_ale_general(m, want)
+        got = f.copy()
+        ch = harness.HandleChain(m, got)
+        assert ch.step() == 10
+        ch.fetch("fct_ttf_max", "fct_ttf_min")
+        ch.free()
+        check(got, want)
+
+
 def test_reference_named_entry_points(abi, oracle_mod):
     """fct_ale_a{1,2,3,4}_reference_ / fct_ale_pre_comm_ keep the reference's names and host-array
     signatures but run on the GPU; checked against the golden vectors of src/reference.cpp."""

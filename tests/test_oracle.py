@@ -95,3 +95,90 @@ def test_limiter_properties(oracle_mod, mesh_mod):
     assert (g.fct_adf_v * f.fct_adf_v >= 0).all()
     for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz"):
         assert bits_equal(getattr(g, k)[~act], getattr(f, k)[~act]), k
+
+
+# ---- vlimit 2 / 3 and iter_yn (parity unpinned by the reference) -------
+def listing_a3_vlimit(m, f, vlimit):
+    """Second, independent restatement of docs/refactoring.md:113-148 in plain Python loops (1-based
+    like the listing), used to cross-check the C oracle on small meshes."""
+    tmax, tmin = f.fct_ttf_max.copy(), f.fct_ttf_min.copy()
+    uv = f.UV_rhs.reshape(m.myDim_elem2D, m.L, 2)
+    for n in range(m.myDim_nod2D):
+        nlev = int(m.nlevels_nod2D[n])
+        ring = m.nod_in_elem2D[n, :m.nod_in_elem2D_num[n]] - 1
+        tv_max = {nz: max(uv[e, nz - 1, 0] for e in ring) for nz in range(1, nlev)}
+        tv_min = {nz: min(uv[e, nz - 1, 1] for e in ring) for nz in range(1, nlev)}
+        for nz in range(2, nlev - 1):
+            col = f.fct_ttf_max[n, nz - 2:nz + 1]       # fct_ttf_max(nz-1:nz+1, n), a1 values
+            if vlimit == 2:
+                tv_max[nz] = max(tv_max[nz], col.max())
+                tv_min[nz] = min(tv_min[nz], col.min())
+            else:
+                tv_max[nz] = min(tv_max[nz], col.max())
+                tv_min[nz] = max(tv_min[nz], col.min())
+        for nz in range(1, nlev):
+            tmax[n, nz - 1] = tv_max[nz] - f.fct_LO[n, nz - 1]
+            tmin[n, nz - 1] = tv_min[nz] - f.fct_LO[n, nz - 1]
+    return tmax, tmin
+
+
+@pytest.mark.parametrize("vlimit", [2, 3])
+def test_oracle_vlimit_matches_listing(oracle_mod, mesh_mod, vlimit):
+    for m, f in (mesh_mod.adversarial_case(60, 12, seed=3), (mesh_mod.make_workload("tiny"), None)):
+        if f is None:
+            f = mesh_mod.make_fields(m)
+        f.vlimit = vlimit
+        oracle_mod.a1(m, f)
+        oracle_mod.a2(m, f)
+        want_max, want_min = listing_a3_vlimit(m, f, vlimit)
+        wide = f.copy()
+        wide.vlimit = 1
+        oracle_mod.a3_vlimit(m, f)
+        assert bits_equal(f.fct_ttf_max, want_max) and bits_equal(f.fct_ttf_min, want_min)
+        oracle_mod.a3(m, wide)
+        assert not bits_equal(f.fct_ttf_max, wide.fct_ttf_max)      # the branches differ from vlimit 1
+
+
+def test_oracle_iterative_branch(oracle_mod, mesh_mod):
+    """iter_yn: limited + rejected parts restore the flux, the surface and bottom vertical levels of
+    fct_adf_v2 are never written (md:228-230), the low-order update follows the listing's order."""
+    m = mesh_mod.make_workload("pi")
+    f = mesh_mod.make_fields(m)
+    f.iter_yn = True
+    rng = np.random.default_rng(5)
+    f.fct_adf_v2 = rng.standard_normal(f.fct_adf_v.shape)
+    f.fct_adf_h2 = rng.standard_normal(f.fct_adf_h.shape)
+    g = f.copy()
+    g.iter_yn = False
+    oracle_mod.pre_comm(m, g)
+    lim = g.copy()
+    oracle_mod.b3_vertical(m, lim)
+    oracle_mod.b3_horizontal(m, lim)
+    h = g.copy()
+    oracle_mod.b3_vertical_iter(m, h)
+    oracle_mod.b3_horizontal_iter(m, h)
+    assert bits_equal(h.fct_adf_v, lim.fct_adf_v) and bits_equal(h.fct_adf_h, lim.fct_adf_h)
+    N, L = m.myDim_nod2D, m.L
+    z = np.arange(m.nl)[None, :]
+    inner = (z >= 1) & (z < (m.nlevels_nod2D[:N, None] - 1))
+    assert rel_err((h.fct_adf_v + h.fct_adf_v2)[inner], g.fct_adf_v[inner], floor=1e-3) < 1e-14
+    assert bits_equal(h.fct_adf_v2[~inner], f.fct_adf_v2[~inner])
+    eact = np.arange(L)[None, :] < m.edge_depth()[:, None]
+    assert rel_err((h.fct_adf_h + h.fct_adf_h2)[eact], g.fct_adf_h[eact], floor=1e-3) < 1e-14
+    # low-order update in numpy, same order of operations (vertical, then edges ascending)
+    lo = h.fct_LO.copy()
+    act = np.arange(L)[None, :] < (m.nlevels_nod2D[:N, None] - 1)
+    v = h.fct_adf_v
+    lo[:N] = np.where(act, lo[:N] + (v[:N, :L] - v[:N, 1:]) * f.dt / f.area[:N, :L] / f.hnode_new[:N], lo[:N])
+    for g_ in range(m.myDim_edge2D):
+        n1, n2 = m.edges[g_] - 1
+        d = int(m.edge_depth()[g_])
+        lo[n1, :d] = lo[n1, :d] + h.fct_adf_h[g_, :d] * f.dt / f.area[n1, :d] / f.hnode_new[n1, :d]
+        lo[n2, :d] = lo[n2, :d] - h.fct_adf_h[g_, :d] * f.dt / f.area[n2, :d] / f.hnode_new[n2, :d]
+    oracle_mod.lo_update(m, h)
+    assert bits_equal(h.fct_LO, lo)
+    # the composed subroutine ends with fct_adf_* = fct_adf_*2
+    full = f.copy()
+    oracle_mod.fct_ale_general(m, full)
+    assert bits_equal(full.fct_adf_v, h.fct_adf_v2) and bits_equal(full.fct_adf_h, h.fct_adf_h2)
+    assert bits_equal(full.fct_LO, lo)

@@ -32,12 +32,16 @@ for TN, cap, nch, wa, wb, npw in cfgs:
         e1.record(df.stream)
         return e1.ms_since(e0) / reps
     try:
-        tot = 0
-        for stage, alg in (("phaseA_warp", algA), ("phaseB_warp", algB)):
-            ms = timeit(lambda: df.stage(stage, f, sync=False))
-            tot += ms
-            print(f"  TN={TN:3d} cap={cap:3d}K stages={nch} warps={wa}/{wb} issuers={npw} {stage}: {ms*1e3:8.1f} us  {alg/ms/1e6:7.1f} GB/s {alg/ms/1e6/65.472:5.1f}%", flush=True)
-        print(f"  -> step {tot*1e3:8.1f} us  {Sn/tot/1e6:6.2f} G upd/s  {(algA+algB)/tot/1e6/65.472:5.1f}% of 6547 GB/s (plan {time.time()-t0:.1f}s)", flush=True)
+        # SWEEP_OPTS: scheduling options of the kernels (knob WT_OPT, read at every launch)
+        for opt in [int(v) for v in os.environ.get("SWEEP_OPTS", "-1").split(",")]:
+            if opt >= 0:
+                abi.tune("WT_OPT", opt)
+            tot = 0
+            for stage, alg in (("phaseA_warp", algA), ("phaseB_warp", algB)):
+                ms = timeit(lambda: df.stage(stage, f, sync=False))
+                tot += ms
+                print(f"  TN={TN:3d} cap={cap:3d}K stages={nch} warps={wa}/{wb} issuers={npw} opt={opt} {stage}: {ms*1e3:8.1f} us  {alg/ms/1e6:7.1f} GB/s {alg/ms/1e6/65.472:5.1f}%", flush=True)
+            print(f"  -> step {tot*1e3:8.1f} us  {Sn/tot/1e6:6.2f} G upd/s  {(algA+algB)/tot/1e6/65.472:5.1f}% of 6547 GB/s (plan {time.time()-t0:.1f}s)", flush=True)
     except abi.AbiError as ex:
         print("  cfg", TN, cap, nch, wa, wb, npw, "failed:", ex)
     df.free(); plan.free()
