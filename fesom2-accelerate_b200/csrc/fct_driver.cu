@@ -319,6 +319,8 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
         T.blob_off = upload_vec(p, h[s].blob_off);
         T.ntiles = h[s].ntiles;
         T.smem_bytes = h[s].smem_bytes;
+        T.max_copies = 0;
+        for (int t = 0; t < h[s].ntiles; ++t) T.max_copies = std::max(T.max_copies, (int)h[s].blob[h[s].blob_off[t]].x);
         if (!T.blob || !T.blob_off) return;
         if (verbose && h[s].ntiles > 0)
             std::fprintf(stderr,
@@ -364,6 +366,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     WarpTilesDev T = packed ? p->wtiles_pk[which] : p->wtiles[which];
     T.diag = env_int("FCT_WT_DIAG", 0);
     T.opt = env_int("FCT_WT_OPT", 2);   // measured (gpurun_out/s6_sweep_mid.log): 2 is +10 % on phase A, 1 neutral
+    if (T.max_copies > WT_PRE_MAX_COPIES || T.diag != 0) T.opt &= ~4;
     if (T.ntiles <= 0) return true;
     if (!packed && (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch)) {
         std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");

@@ -55,13 +55,20 @@ struct WarpTilesDev {
     int smem_bytes;             // shared memory of one stage (max over tiles)
     int diag;                   // timing experiments only (wrong results): 1 skip the edge-row copies, 2 skip all row copies
     int opt;                    // scheduling options (results unaffected): 1 producers wait suspended in hardware
-                                // instead of polling, 2 consumers issue a tile's first loads before waiting for its rows
+                                // instead of polling, 2 consumers issue a tile's first loads before waiting for its rows,
+                                // 4 copy lists travel ahead of their blobs (needs max_copies <= WT_PRE_MAX_COPIES)
+    int max_copies;             // longest copy list of a tile
 };
 
 // warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A WT_CONVERTERS a1 converters, then NWC
 // consumers (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128 per
 // thread, 20 -> 96, 24 -> 80)
-constexpr int WT_SMEM_HEAD = 256;     // mbarriers + per-stage counters in front of the stages
+// Head of a blob (header + copy list) copied ahead of the blob itself into a slot of its own, one
+// per stage: the issuer warps pull the tile's rows into L2 while the stage is still being computed
+// and start the bulk copies the moment it is released, next to the blob's copy instead of after it.
+constexpr int WT_PRE_BYTES = 1024;
+constexpr int WT_SMEM_CTRL = 256;     // mbarriers + per-stage counters
+constexpr int WT_SMEM_HEAD = WT_SMEM_CTRL + 4 * WT_PRE_BYTES;   // in front of the stages
 #ifndef WT_IDLE_NS
 #define WT_IDLE_NS 400                // sleep of an idle producer between two probes of its barrier
 #endif
@@ -80,6 +87,7 @@ constexpr int WT_SMEM_MAX = 227 * 1024;
 //              depth | writer << 30 | second << 31, global element offset of the edge row}
 // schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
 constexpr int WT_HDR_BYTES = 64;
+constexpr int WT_PRE_MAX_COPIES = (WT_PRE_BYTES - WT_HDR_BYTES) / 8;
 constexpr unsigned WT_IDLE = 0xffffu;
 
 // ---- PTX: mbarrier + 1-D bulk copy (TMA) ---------------------------------------------------------
@@ -622,22 +630,29 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
     extern __shared__ __align__(128) unsigned char wt_sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar = smem_u32(wt_sm);
-    // barriers: [0,NSTAGE) stage empty, [NSTAGE,2N) blob landed, [2N,3N) rows landed, [3N,4N) a1 done
+    // barriers: [0,NSTAGE) stage empty, [NSTAGE,2N) blob landed, [2N,3N) rows landed, [3N,4N) a1 done,
+    // [4N,5N) copy list landed in its slot, [5N,6N) copy list consumed
     auto b_empty = [&](int s) { return bar + 8u * s; };
     auto b_blob = [&](int s) { return bar + 8u * (NSTAGE + s); };
     auto b_rows = [&](int s) { return bar + 8u * (2 * NSTAGE + s); };
     auto b_ready = [&](int s) { return bar + 8u * (3 * NSTAGE + s); };
-    int *next_item = reinterpret_cast<int *>(wt_sm + 8 * 4 * NSTAGE);
+    auto b_pre = [&](int s) { return bar + 8u * (4 * NSTAGE + s); };
+    auto b_prefree = [&](int s) { return bar + 8u * (5 * NSTAGE + s); };
+    int *next_item = reinterpret_cast<int *>(wt_sm + 8 * 6 * NSTAGE);
     int *tile_of = next_item + NSTAGE;   // (tile, tracer) index staged in each stage, -1: no more work
     int *tracer_of = tile_of + NSTAGE;   // its tracer (one integer division per tile, not one per warp)
-    static_assert(8 * 4 * NSTAGE + 12 * NSTAGE <= WT_SMEM_HEAD && NSTAGE <= 4, "smem head");
+    int *pre_tracer = tracer_of + NSTAGE;   // tracer of the copy list in each slot, -1: no more work
+    static_assert(8 * 6 * NSTAGE + 16 * NSTAGE <= WT_SMEM_CTRL && NSTAGE <= 4, "smem head");
     const int total = T.ntiles * ntracers;
+    const bool lists_ahead = T.opt & 4;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(b_empty(s), NWC);
             mbar_init(b_blob(s), 1);
             mbar_init(b_rows(s), 1);
             mbar_init(b_ready(s), WT_CONVERTERS);
+            mbar_init(b_pre(s), 1);
+            mbar_init(b_prefree(s), NPW);
         }
         fence_mbar_init();
     }
@@ -659,6 +674,21 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 b1 = __ldg(T.blob_off + v % T.ntiles + 1);
                 // the stage is still busy: have the blob wait in L2
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(T.blob + b0), "r"((b1 - b0) * 16u) : "memory");
+            }
+            if (lists_ahead) {
+                // the copy list goes ahead into its slot as soon as the issuers are done with the slot's last list
+                mbar_wait_idle(b_prefree(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
+                if (lane == 0) {
+                    if (v < total) {
+                        const uint32_t nb = min((b1 - b0) * 16u, (uint32_t)WT_PRE_BYTES);
+                        pre_tracer[s] = v / T.ntiles;
+                        mbar_expect_tx(b_pre(s), nb);
+                        bulk_g2s(smem_u32(wt_sm + WT_SMEM_CTRL + s * WT_PRE_BYTES), T.blob + b0, nb, b_pre(s));
+                    } else {
+                        pre_tracer[s] = -1;
+                        mbar_arrive(b_pre(s));
+                    }
+                }
             }
             mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
             if (v >= total) {
@@ -686,7 +716,40 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         }
     } else if (warp <= NPW) {
         // ---- copy issuers: one bulk copy per staged row, the list shared by NPW warps ----
-        for (int it = 0;; ++it) {
+        for (int it = 0; lists_ahead; ++it) {
+            // list from its own slot: rows pulled into L2 while the stage is still busy, copies issued
+            // the moment it is released (next to the blob's copy, not after it)
+            const int s = it % NSTAGE;
+            mbar_wait_idle(b_pre(s), (it / NSTAGE) & 1, T.opt & 1);
+            const int tr = pre_tracer[s];
+            if (tr < 0) break;
+            const unsigned char *pl = wt_sm + WT_SMEM_CTRL + s * WT_PRE_BYTES;
+            const int n_copies = reinterpret_cast<const int4 *>(pl)[0].x;
+            const int4 h2 = reinterpret_cast<const int4 *>(pl)[2];
+            const int2 *copies = reinterpret_cast<const int2 *>(pl + WT_HDR_BYTES);
+            const double *ga = (PHASE_A ? A.lo : A.plus) + tr * A.ts_node;
+            const double *gb = (PHASE_A ? A.ttf : A.minus) + tr * A.ts_node;
+            const double *ge = A.adf_h_in + tr * A.ts_edge;
+            for (int u = (warp - 1) * 32 + lane; u < n_copies; u += NPW * 32) {
+                const int2 r = copies[u];
+                const uint32_t sz = (((uint32_t)r.y >> 14) & 0x3fffu) << 4, arr = ((uint32_t)r.y >> 28) & 3u;
+                const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(sz) : "memory");
+            }
+            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
+            if (warp == 1 && lane == 0) mbar_expect_tx(b_rows(s), (uint32_t)h2.w);
+            const uint32_t sa = smem_u32(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes + h2.x);
+            for (int u = (warp - 1) * 32 + lane; u < n_copies; u += NPW * 32) {
+                const int2 r = copies[u];
+                const uint32_t so = ((uint32_t)r.y & 0x3fffu) << 4, sz = (((uint32_t)r.y >> 14) & 0x3fffu) << 4;
+                const uint32_t arr = ((uint32_t)r.y >> 28) & 3u;
+                const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
+                bulk_g2s(sa + so, src, sz, b_rows(s));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_prefree(s));
+        }
+        for (int it = 0; !lists_ahead; ++it) {
             const int s = it % NSTAGE;
             mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt & 1);
             if (tile_of[s] < 0) break;

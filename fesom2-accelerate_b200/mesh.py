@@ -467,7 +467,7 @@ def slice_fields(f: Fields, part: Partition) -> Fields:
     for k, v in f.__dict__.items():
         if not isinstance(v, np.ndarray):
             kw[k] = v
-        elif k == "fct_adf_h":
+        elif k in ("fct_adf_h", "fct_adf_h2"):
             kw[k] = v[part.mesh.edge_gid].copy()
         elif k == "UV_rhs":
             kw[k] = v[part.mesh.elem_gid].copy()

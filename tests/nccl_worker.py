@@ -57,6 +57,31 @@ def main():
                 assert np.array_equal(getattr(got, k)[:n], getattr(wants[t], k)[g]), (rank, mode, t, k)
             assert np.array_equal(got.fct_adf_h, wants[t].fct_adf_h[part.mesh.edge_gid]), (rank, mode, t, "fct_adf_h")
         df.free()
+    # vlimit 3 + one pass of the iterative branch (fct_LO halo rows exchanged over NVLink inside the
+    # call), then the closing plain pass: docs/refactoring.md:131-148, :226-290
+    f = fs[0].copy()
+    f.vlimit, f.iter_yn = 3, True
+    f.fct_adf_v2, f.fct_adf_h2 = np.zeros_like(f.fct_adf_v), np.zeros_like(f.fct_adf_h)
+    want = f.copy()
+    lf = mesh_mod.slice_fields(f, part)
+    lf.vlimit = 3
+    df = harness.DeviceFields(plan, 1, with_uv=True)
+    df.upload(lf)
+    for it in (True, False):
+        want.iter_yn = lf.iter_yn = it
+        oracle.fct_ale_general(m, want)
+        assert df.step_general(lf, halo=halo) == 10
+    names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz",
+             "fct_adf_v", "fct_adf_h", "fct_LO"]
+    got = df.download(lf, names=names)
+    for k in names:
+        if k == "fct_adf_h":
+            assert np.array_equal(got.fct_adf_h, want.fct_adf_h[part.mesh.edge_gid]), (rank, "general", k)
+        else:
+            assert np.array_equal(getattr(got, k)[:n], getattr(want, k)[g]), (rank, "general", k)
+    # the exchanged halo rows of fct_LO equal their owners' values
+    assert np.array_equal(got.fct_LO, want.fct_LO[part.mesh.node_gid]), (rank, "fct_LO halo")
+    df.free()
     dist.barrier()
     halo.free()
     plan.free()

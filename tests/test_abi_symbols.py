@@ -67,3 +67,30 @@ def test_no_cpu_fallback_without_a_device(abi, harness, mesh_mod):
         harness.DevicePlan(m)
     with pytest.raises(abi.AbiError):
         harness.HandleChain(m, mesh_mod.make_fields(m))
+
+
+def test_fortran_module_matches_header(abi):
+    """fortran/fesom2_accelerate_b200.f90 (no Fortran compiler in this image): every bind(C) name is a
+    symbol of the header, with as many dummy arguments as the C prototype has parameters, and every
+    Part 2 symbol of the header has an interface."""
+    f90 = open(os.path.join(ROOT, "fortran", "fesom2_accelerate_b200.f90")).read()
+    f90 = re.sub(r"!.*", "", f90)
+    f90 = re.sub(r"&\s*\n\s*&?", " ", f90)
+    bound = {}
+    for m in re.finditer(r"subroutine\s+\w+\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(\w+)\"\)", f90, flags=re.I):
+        bound[m.group(2)] = len([a for a in m.group(1).split(",") if a.strip()])
+    hdr = open(os.path.join(ROOT, "include", "fesom2-accelerate.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+              for m in re.finditer(r"\bvoid\s+(\w+)\s*\(([^)]*)\)\s*;", hdr)}
+    assert len(bound) >= 30
+    for name, nargs in bound.items():
+        assert name in protos, name
+        assert nargs == protos[name], (name, nargs, protos[name])
+    part2 = hdr[hdr.index("Part 2") if "Part 2" in hdr else 0:]
+    part2_syms = set(re.findall(r"\bvoid\s+(\w+_)\s*\(", hdr[hdr.index("fct_ale_c_acc_") - 200:]))
+    missing = part2_syms - set(bound) - {"fct_ale_plan_inspect_"}      # host-side introspection for the tests
+    assert not missing, missing
+    enum = dict(re.findall(r"(FCT_\w+)\s*=\s*(\d+)", hdr))
+    for k, v in re.findall(r"(FCT_\w+)\s*=\s*(\d+)", f90):
+        assert enum[k] == v, k
