@@ -27,7 +27,8 @@ SYMBOLS = [
     "fct_ale_event_elapsed_ms_", "fct_ale_event_destroy_", "fct_ale_mem_info_",
     "fct_ale_plan_create_", "fct_ale_plan_destroy_", "fct_ale_plan_pitch_", "fct_ale_plan_inspect_", "fct_ale_plan_kernels_",
     "fct_ale_fields_create_", "fct_ale_fields_create_packed_", "fct_ale_fields_destroy_", "fct_ale_field_upload_",
-    "fct_ale_field_download_", "fct_ale_field_link_bytes_", "fct_ale_step_", "fct_ale_step_general_", "fct_ale_halo_exchange_field_", "fct_ale_stage_",
+    "fct_ale_field_download_", "fct_ale_field_link_bytes_", "fct_ale_step_", "fct_ale_step_general_", "fct_ale_halo_exchange_field_",
+    "stress2rhs_plan_create_", "stress2rhs_plan_destroy_", "stress2rhs_acc_", "stress2rhs_", "fct_ale_stage_",
     "fct_ale_comm_unique_id_", "fct_ale_halo_create_", "fct_ale_halo_destroy_",
     "fct_ale_halo_exchange_",
 ]

@@ -400,3 +400,67 @@ class DeviceFields:
         st = C.c_int()
         self.lib.fct_ale_fields_destroy_(C.byref(self.h), C.byref(st))
         self.stream.free()
+
+
+# --------------------------------------------------------------------------------------------
+# stress2rhs: device-resident through handles, or host arrays in / out
+# --------------------------------------------------------------------------------------------
+STRESS_INPUTS = ("ice_strength", "elem_area", "sigma11", "sigma12", "sigma22", "gradient_sca", "metric_factor",
+                 "inv_areamass", "rhs_a", "rhs_m")
+
+
+class StressChain:
+    """stress2rhs_plan_create_ + handles of alloc_var_ + stress2rhs_acc_ (asynchronous)."""
+
+    def __init__(self, d):
+        self.lib = abi.load()
+        self.d = d
+        self.plan = C.c_void_p()
+        st = C.c_int()
+        en = np.ascontiguousarray(d["elem2D_nodes"], dtype=np.int32)
+        self.lib.stress2rhs_plan_create_(C.byref(self.plan), ci(d["N"]), ci(d["E"]), ci(en.shape[1]),
+                                         iptr(en.reshape(-1)), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("stress2rhs_plan_create_ failed")
+        self.stream = abi.Stream()
+        self.u, self.v = np.full(d["N"], np.nan), np.full(d["N"], np.nan)
+        self.vars = {k: abi.Var(d[k]) for k in STRESS_INPUTS}
+        self.vars["U"], self.vars["V"] = abi.Var(self.u), abi.Var(self.v)
+        for k in STRESS_INPUTS:
+            self.vars[k].upload()
+
+    def run(self, sync=True):
+        v, st = self.vars, C.c_int()
+        self.lib.stress2rhs_acc_(C.byref(self.plan), self.stream.ref, v["U"].ref, v["V"].ref, *[v[k].ref for k in STRESS_INPUTS],
+                                 C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("stress2rhs_acc_ failed")
+        if sync:
+            self.stream.sync()
+
+    def fetch(self):
+        self.vars["U"].download()
+        self.vars["V"].download()
+        return self.u, self.v
+
+    def free(self):
+        for v in self.vars.values():
+            v.free()
+        st = C.c_int()
+        self.lib.stress2rhs_plan_destroy_(C.byref(self.plan), C.byref(st))
+        self.stream.free()
+
+
+def stress2rhs_host(d):
+    """stress2rhs_ on host arrays (the argument order of src/reference.cpp:440)."""
+    lib = abi.load()
+    u, v = np.full(d["N"], np.nan), np.full(d["N"], np.nan)
+    st = C.c_int()
+    en = np.ascontiguousarray(d["elem2D_nodes"], dtype=np.int32)
+    lib.stress2rhs_(ci(d["N"]), ci(d["E"]), ci(en.shape[1]), dptr(u), dptr(v), dptr(d["ice_strength"]),
+                    iptr(en.reshape(-1)), dptr(d["elem_area"]), dptr(d["sigma11"]), dptr(d["sigma12"]),
+                    dptr(d["sigma22"]), dptr(d["gradient_sca"]), dptr(d["metric_factor"]),
+                    dptr(d["inv_areamass"]), dptr(d["rhs_a"]), dptr(d["rhs_m"]), C.byref(st))
+    if st.value != 0:
+        raise abi.AbiError("stress2rhs_ failed")
+    return u, v

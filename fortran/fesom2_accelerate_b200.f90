@@ -182,6 +182,39 @@ module fesom2_accelerate_b200
       integer(c_int) :: field, istat
     end subroutine
 
+    ! ---- stress2rhs (EVP sea ice; replaces src/reference.cpp:440-480) ----
+    ! elem2D_nodes: 0-based, (elem2D_nodes_size, 3) seen from Fortran, as the reference indexes it
+    subroutine stress2rhs_plan_create(plan, myDim_nod2D, myDim_elem2D, elem2D_nodes_size, elem2D_nodes, istat) &
+                                      bind(C, name="stress2rhs_plan_create_")
+      import :: c_int, c_ptr
+      type(c_ptr) :: plan
+      integer(c_int) :: myDim_nod2D, myDim_elem2D, elem2D_nodes_size, istat
+      integer(c_int) :: elem2D_nodes(*)
+    end subroutine
+    subroutine stress2rhs_plan_destroy(plan, istat) bind(C, name="stress2rhs_plan_destroy_")
+      import :: c_int, c_ptr
+      type(c_ptr) :: plan
+      integer(c_int) :: istat
+    end subroutine
+    subroutine stress2rhs_acc(plan, stream, U_rhs_ice, V_rhs_ice, ice_strength, elem_area, sigma11, sigma12, &
+                              sigma22, gradient_sca, metric_factor, inv_areamass, rhs_a, rhs_m, istat)        &
+                              bind(C, name="stress2rhs_acc_")
+      import :: c_int, c_ptr
+      type(c_ptr) :: plan, stream, U_rhs_ice, V_rhs_ice, ice_strength, elem_area, sigma11, sigma12, sigma22, &
+                     gradient_sca, metric_factor, inv_areamass, rhs_a, rhs_m
+      integer(c_int) :: istat
+    end subroutine
+    subroutine stress2rhs_host(myDim_nod2D, myDim_elem2D, elem2D_nodes_size, U_rhs_ice, V_rhs_ice,          &
+                               ice_strength, elem2D_nodes, elem_area, sigma11, sigma12, sigma22,             &
+                               gradient_sca, metric_factor, inv_areamass, rhs_a, rhs_m, istat)               &
+                               bind(C, name="stress2rhs_")
+      import :: c_int, c_double
+      integer(c_int) :: myDim_nod2D, myDim_elem2D, elem2D_nodes_size, istat
+      integer(c_int) :: elem2D_nodes(*)
+      real(c_double) :: U_rhs_ice(*), V_rhs_ice(*), ice_strength(*), elem_area(*), sigma11(*), sigma12(*),   &
+                        sigma22(*), gradient_sca(*), metric_factor(*), inv_areamass(*), rhs_a(*), rhs_m(*)
+    end subroutine
+
     ! ---- events, introspection, tuning ----
     subroutine fct_ale_event_create(event, istat) bind(C, name="fct_ale_event_create_")
       import :: c_int, c_ptr

@@ -301,6 +301,26 @@ void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *ista
  * the iterative branch, FCT_TTF, ...): owned-boundary rows -> the neighbours' halo rows */
 void fct_ale_halo_exchange_field_(void **fields, void **halo, void **stream, int *field, int *istat);
 
+/* ---- stress2rhs: divergence of the sea-ice stress tensor into the rhs vectors ---------------- */
+/* SURVEY.md section 8(f) row 4.  Replaces the reference's CPU restatement src/reference.cpp:440-480
+ * (docs/refactoring.md:409-461; the reference has no GPU kernel for it): the element -> node
+ * scatter runs as a deterministic node-centric gather in ascending element order, bit-identical to
+ * the sequential loop.  Index conventions are reference.cpp's: elem2D_nodes 0-based with element
+ * stride *elem2D_nodes_size ([3][size]), gradient_sca addressed corner*6 + element (at least
+ * myDim_elem2D + 30 entries); nodes >= myDim_nod2D (halo corners) are not written. */
+void stress2rhs_plan_create_(void **plan, int *myDim_nod2D, int *myDim_elem2D, int *elem2D_nodes_size,
+                             int *elem2D_nodes, int *istat);
+void stress2rhs_plan_destroy_(void **plan, int *istat);
+/* device-resident: every array a handle of alloc_var_ / reserve_var_; asynchronous on *s */
+void stress2rhs_acc_(void **plan, void **s, void **U_rhs_ice, void **V_rhs_ice, void **ice_strength,
+                     void **elem_area, void **sigma11, void **sigma12, void **sigma22, void **gradient_sca,
+                     void **metric_factor, void **inv_areamass, void **rhs_a, void **rhs_m, int *istat);
+/* host arrays in, host arrays out (synchronous; argument order of reference.cpp:440) */
+void stress2rhs_(int *myDim_nod2D, int *myDim_elem2D, int *elem2D_nodes_size, real_type *U_rhs_ice,
+                 real_type *V_rhs_ice, real_type *ice_strength, int *elem2D_nodes, real_type *elem_area,
+                 real_type *sigma11, real_type *sigma12, real_type *sigma22, real_type *gradient_sca,
+                 real_type *metric_factor, real_type *inv_areamass, real_type *rhs_a, real_type *rhs_m, int *istat);
+
 #ifdef __cplusplus
 }
 #endif

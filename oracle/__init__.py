@@ -201,6 +201,49 @@ def fct_ale_general(m, f, exchange=None):
     f.fct_adf_v[...] = f.fct_adf_v2
 
 
+# ------------------------------------------------------------------ stress2rhs
+STRESS_KEYS = ("ice_strength", "elem_area", "sigma11", "sigma12", "sigma22", "gradient_sca", "metric_factor",
+               "inv_areamass", "rhs_a", "rhs_m")
+
+
+def stress_case(n_nodes, n_elems, seed=0, elem_nodes=None):
+    """Seeded inputs of stress2rhs in the layout src/reference.cpp:440-480 indexes: 0-based
+    elem2D_nodes[3][E], gradient_sca with 6*E entries (the reference reads up to index 29+E)."""
+    rng = np.random.default_rng(seed)
+    d = {"N": n_nodes, "E": n_elems}
+    d["elem2D_nodes"] = (rng.integers(0, n_nodes, (3, n_elems)) if elem_nodes is None else elem_nodes).astype(np.int32)
+    d["ice_strength"] = np.where(rng.random(n_elems) < 0.8, rng.random(n_elems) * 1e4, 0.0)
+    d["elem_area"] = rng.uniform(1e7, 1e9, n_elems)
+    for k in ("sigma11", "sigma12", "sigma22"):
+        d[k] = rng.standard_normal(n_elems) * 1e3
+    d["gradient_sca"] = rng.standard_normal(6 * max(n_elems, 6)) * 1e-5
+    d["metric_factor"] = rng.standard_normal(n_elems) * 1e-7
+    d["inv_areamass"] = np.where(rng.random(n_nodes) < 0.9, rng.uniform(1e-12, 1e-9, n_nodes), 0.0)
+    d["rhs_a"] = rng.standard_normal(n_nodes)
+    d["rhs_m"] = rng.standard_normal(n_nodes)
+    return d
+
+
+def stress2rhs(d):
+    u, v = np.full(d["N"], np.nan), np.full(d["N"], np.nan)
+    lib().oracle_stress2rhs(C.c_int(d["N"]), C.c_int(d["E"]), C.c_int(d["elem2D_nodes"].shape[1]), _d(u), _d(v),
+                            _d(d["ice_strength"]), _i(d["elem2D_nodes"].reshape(-1)), _d(d["elem_area"]),
+                            _d(d["sigma11"]), _d(d["sigma12"]), _d(d["sigma22"]), _d(d["gradient_sca"]),
+                            _d(d["metric_factor"]), _d(d["inv_areamass"]), _d(d["rhs_a"]), _d(d["rhs_m"]))
+    return u, v
+
+
+def ref_stress2rhs(d):
+    """The reference's own function (C++ linkage, by-value scalars: reference.cpp:440)."""
+    fn = getattr(ref(), "_Z10stress2rhsiiiPdS_S_PiS_S_S_S_S_S_S_S_S_")
+    u, v = np.full(d["N"], np.nan), np.full(d["N"], np.nan)
+    fn(C.c_int(d["N"]), C.c_int(d["E"]), C.c_int(d["elem2D_nodes"].shape[1]), _d(u), _d(v),
+       _d(d["ice_strength"]), _i(d["elem2D_nodes"].reshape(-1)), _d(d["elem_area"]), _d(d["sigma11"]),
+       _d(d["sigma12"]), _d(d["sigma22"]), _d(d["gradient_sca"]), _d(d["metric_factor"]),
+       _d(d["inv_areamass"]), _d(d["rhs_a"]), _d(d["rhs_m"]))
+    return u, v
+
+
 # ------------------------------------------------------------------ the reference's own code
 def _ci(v):
     return C.byref(C.c_int(v))

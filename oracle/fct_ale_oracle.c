@@ -426,3 +426,45 @@ void oracle_lo_update(int n_nodes, int n_edges, int nl, const int *nlev_nod, con
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * stress2rhs: src/reference.cpp:440-480, docs/refactoring.md:409-461.
+ * Same index expressions as the reference: 0-based elem2D_nodes with element stride
+ * elem2D_nodes_size (reference.cpp:457) and gradient_sca addressed "corner*6 + element"
+ * (reference.cpp:460-461).  Pinned against the reference's own compiled function
+ * (tests/test_oracle.py, tests/golden/ref_cpp_stress2rhs.npz).
+ * ------------------------------------------------------------------------------------------------ */
+void oracle_stress2rhs(int n_nodes, int n_elems, int en_size, double *u_rhs, double *v_rhs,
+                       const double *ice_strength, const int *elem_nodes, const double *elem_area,
+                       const double *sigma11, const double *sigma12, const double *sigma22,
+                       const double *gradient_sca, const double *metric_factor,
+                       const double *inv_areamass, const double *rhs_a, const double *rhs_m)
+{
+    const double one_third = 1.0 / 3.0;
+    for (int n = 0; n < n_nodes; ++n) {
+        u_rhs[n] = 0.0;
+        v_rhs[n] = 0.0;
+    }
+    for (int e = 0; e < n_elems; ++e) {
+        if (ice_strength[e] > 0.0) {
+            for (int k = 0; k < 3; ++k) {
+                const int node = elem_nodes[(size_t)k * en_size + e];
+                u_rhs[node] -= elem_area[e] * ((sigma11[e] * gradient_sca[k * 6 + e])
+                                               + (sigma12[e] * gradient_sca[(k + 3) * 6 + e])
+                                               + (sigma12[e] * one_third * metric_factor[e]));
+                v_rhs[node] -= elem_area[e] * ((sigma12[e] * gradient_sca[k * 6 + e])
+                                               + (sigma22[e] * gradient_sca[(k + 3) * 6 + e])
+                                               - (sigma11[e] * one_third * metric_factor[e]));
+            }
+        }
+    }
+    for (int n = 0; n < n_nodes; ++n) {
+        if (inv_areamass[n] > 0.0) {
+            u_rhs[n] = (u_rhs[n] * inv_areamass[n]) + rhs_a[n];
+            v_rhs[n] = (v_rhs[n] * inv_areamass[n]) + rhs_m[n];
+        } else {
+            u_rhs[n] = 0.0;
+            v_rhs[n] = 0.0;
+        }
+    }
+}

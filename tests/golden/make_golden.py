@@ -15,6 +15,9 @@ Two kinds of golden vectors, both produced by the REFERENCE's own code on seeded
    to one common stride before the call (documented per case below) -- the arithmetic per cell is
    what is pinned.
 
+3. `ref_cpp_stress2rhs.npz` -- outputs of the reference's stress2rhs (src/reference.cpp:440-480, the
+   same compiled library).
+
 The inputs are stored next to the outputs, so the tests never depend on the generator staying
 bit-stable.
 """
@@ -121,6 +124,17 @@ def gen_ref_numpy(m, f):
     print("wrote ref_numpy_tiny")
 
 
+def gen_ref_stress2rhs():
+    """stress2rhs through the reference's own compiled function (src/reference.cpp:440-480) on the
+    connectivity of the tiny mesh, 0-based [3][E] as that function indexes it."""
+    m = mesh_mod.make_workload("tiny", seed=0)
+    tri = np.ascontiguousarray((m.elem2D_nodes - 1).T)
+    d = oracle.stress_case(m.myDim_nod2D, m.myDim_elem2D, seed=7, elem_nodes=tri)
+    d["U_rhs_ice"], d["V_rhs_ice"] = oracle.ref_stress2rhs(d)
+    np.savez_compressed(os.path.join(OUT, "ref_cpp_stress2rhs.npz"), **d)
+    print("wrote stress2rhs", d["N"], d["E"])
+
+
 def main():
     oracle.build()
     assert oracle.have_ref(), "oracle/_ref/libref.so missing"
@@ -130,6 +144,7 @@ def main():
     gen_ref_numpy(m, f)
     ma, fa = mesh_mod.adversarial_case(96, 12, seed=3)
     gen_ref_cpp("adversarial", ma, fa)
+    gen_ref_stress2rhs()
 
 
 if __name__ == "__main__":

@@ -4,6 +4,8 @@
   functions (b3 / c) -- tests/golden/make_golden.py;
 * live comparison with oracle/_ref/libref.so (the reference compiled unmodified) when present.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -182,3 +184,23 @@ def test_oracle_iterative_branch(oracle_mod, mesh_mod):
     oracle_mod.fct_ale_general(m, full)
     assert bits_equal(full.fct_adf_v, h.fct_adf_v2) and bits_equal(full.fct_adf_h, h.fct_adf_h2)
     assert bits_equal(full.fct_LO, lo)
+
+
+# ---- stress2rhs: pinned to the reference's compiled function ----------
+def test_oracle_stress2rhs_matches_golden(oracle_mod):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_cpp_stress2rhs.npz"))
+    d = {k: z[k] for k in z.files}
+    d["N"], d["E"] = int(z["N"]), int(z["E"])
+    u, v = oracle_mod.stress2rhs(d)
+    assert bits_equal(u, z["U_rhs_ice"]) and bits_equal(v, z["V_rhs_ice"])
+    assert np.count_nonzero(u) > d["N"] // 2
+
+
+def test_oracle_stress2rhs_matches_libref_live(oracle_mod, mesh_mod):
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    m = mesh_mod.make_workload("pi")
+    tri = np.ascontiguousarray((m.elem2D_nodes - 1).T)          # 0-based [3][E], reference.cpp:457
+    for d in (oracle_mod.stress_case(500, 1300, seed=1), oracle_mod.stress_case(m.myDim_nod2D, m.myDim_elem2D, seed=2, elem_nodes=tri)):
+        a, b = oracle_mod.stress2rhs(d), oracle_mod.ref_stress2rhs(d)
+        assert bits_equal(a[0], b[0]) and bits_equal(a[1], b[1])
