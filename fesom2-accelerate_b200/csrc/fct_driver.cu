@@ -352,6 +352,12 @@ static const WarpVariant g_wvariants[] = {
     WT_VB(3, 19, 4), WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 17, 6), WT_VB(3, 21, 2),
     WT_VB(2, 19, 4), WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(4, 19, 4), WT_VB(4, 17, 6),
 };
+// phase A with vlimit 2 / 3 (docs/refactoring.md:113-148): the default shapes of the packed and of
+// the padded layout for every ring depth
+#define WT_VL(S, C, I) {k_phase_warp<true, S, C, I, false>, true, S, C, I}
+static const WarpVariant g_wvariants_vl[] = {
+    WT_VL(3, 19, 2), WT_VL(3, 17, 4), WT_VL(2, 17, 4), WT_VL(4, 17, 4),
+};
 
 
 // which: 0 all owned nodes, 1 boundary list, 2 interior list
@@ -386,18 +392,24 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // 24 warps in all at 80 registers; the packed layout needs a sixth of the bulk copies: two issuers
     npw = npw <= 0 ? (packed ? 2 : 4) : npw;
     nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
-    constexpr int NV = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
+    constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
+    constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
+    constexpr int NV = NV1 + NVL;
+    const bool vl = isA && A.vlimit != 1 && A.vlimit != 0;
+    const WarpVariant *table = vl ? g_wvariants_vl : g_wvariants;
     int vi = -1, best = 1 << 30;
-    for (int i = 0; i < NV; ++i) {
-        if (g_wvariants[i].stages != stages || g_wvariants[i].phase_a != isA) continue;
-        const int dist = 4 * std::abs(g_wvariants[i].consumers - nwc) + std::abs(g_wvariants[i].issuers - npw);
+    for (int i = 0; i < (vl ? NVL : NV1); ++i) {
+        if (table[i].stages != stages || table[i].phase_a != isA) continue;
+        const int dist = 4 * std::abs(table[i].consumers - nwc) + std::abs(table[i].issuers - npw);
         if (dist < best) {
             best = dist;
             vi = i;
         }
     }
+    if (vi < 0) return false;
     const int ph = isA ? 0 : 1;
-    const WarpVariant &v = g_wvariants[vi];
+    const WarpVariant &v = table[vi];
+    if (vl) vi += NV1;   // slot in the attribute table below
     const size_t smem = WT_SMEM_HEAD + (size_t)stages * stage_bytes;
     static size_t attr_set[2][NV] = {};
     if (smem > attr_set[ph][vi]) {

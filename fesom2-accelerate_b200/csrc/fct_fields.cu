@@ -178,6 +178,51 @@ static bool run_stage(Fields *f, const Arrays &A, int stage, const int *list, in
     return launch_stage(stage, 2, A, f->plan->dev, list, first, count, f->T, s);
 }
 
+// The two fused phases of one step (modes 1, 2, 3 of fct_ale_step_), overlapped with the halo exchange
+// when there is one.  A.vlimit selects the a3 variant of the warp-item phase A.
+static void fused_step(Fields *f, Halo *h, cudaStream_t s, const Arrays &A, int mode, int *alg_state)
+{
+    const Plan *p = f->plan;
+    const int N = p->N;
+    const bool warped = (f->packed ? p->wtiles_pk_ok : p->wtiles_ok) && mode == 1;
+    const bool tiled = p->tiles_ok && (mode == 3 || (mode == 1 && !warped));
+    if (A.vlimit != 1 && !warped) {
+        std::fprintf(stderr, "fesom2-accelerate: vlimit 2 / 3 are fused in the warp-item kernels only\n");
+        return;
+    }
+    // one fused phase over a node set: 0 all owned, 1 boundary, 2 interior
+    auto phase = [&](int stage, int which) -> bool {
+        if (warped) return launch_warp(stage, A, p, which, f->T, s);
+        if (tiled) return launch_tile(stage, A, p, which, f->T, s);
+        if (which == 0) return run_stage(f, A, stage, nullptr, 0, N, s);
+        return which == 1 ? run_stage(f, A, stage, p->d_boundary, 0, p->n_boundary, s)
+                          : run_stage(f, A, stage, p->d_interior, 0, p->n_interior, s);
+    };
+    if (!h) {
+        if (!phase(ST_PHASE_A, 0)) return;
+        *alg_state = 6;
+        if (!phase(ST_PHASE_B, 0)) return;
+        *alg_state = 10;
+        return;
+    }
+    // Overlapped schedule: the boundary nodes' factors are computed first and travel over NVLink
+    // on the halo's own stream while the interior nodes run phase A and phase B; the boundary
+    // nodes' phase B (the only consumer of remote factors) comes last.
+    cudaStream_t c = halo_comm_stream(h);
+    if (!phase(ST_PHASE_A, 1)) return;
+    if (!cuda_ok(cudaEventRecord(halo_event(h, 0), s), "event") ||
+        !cuda_ok(cudaStreamWaitEvent(c, halo_event(h, 0), 0), "wait"))
+        return;
+    if (!halo_exchange(f, h, c)) return;
+    if (!cuda_ok(cudaEventRecord(halo_event(h, 1), c), "event")) return;
+    if (!phase(ST_PHASE_A, 2)) return;
+    *alg_state = 6;
+    if (!phase(ST_PHASE_B, 2)) return;
+    if (!cuda_ok(cudaStreamWaitEvent(s, halo_event(h, 1), 0), "wait")) return;
+    if (!phase(ST_PHASE_B, 1)) return;
+    *alg_state = 10;
+}
+
 }   // namespace fct
 
 using namespace fct;
@@ -506,39 +551,7 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
         }
         return;
     }
-    const bool warped = (f->packed ? p->wtiles_pk_ok : p->wtiles_ok) && *mode == 1;
-    const bool tiled = p->tiles_ok && (*mode == 3 || (*mode == 1 && !warped));
-    // one fused phase over a node set: 0 all owned, 1 boundary, 2 interior
-    auto phase = [&](int stage, int which) -> bool {
-        if (warped) return launch_warp(stage, A, p, which, f->T, s);
-        if (tiled) return launch_tile(stage, A, p, which, f->T, s);
-        if (which == 0) return run_stage(f, A, stage, nullptr, 0, N, s);
-        return which == 1 ? run_stage(f, A, stage, p->d_boundary, 0, p->n_boundary, s)
-                          : run_stage(f, A, stage, p->d_interior, 0, p->n_interior, s);
-    };
-    if (!h) {
-        if (!phase(ST_PHASE_A, 0)) return;
-        *alg_state = 6;
-        if (!phase(ST_PHASE_B, 0)) return;
-        *alg_state = 10;
-        return;
-    }
-    // Overlapped schedule: the boundary nodes' factors are computed first and travel over NVLink
-    // on the halo's own stream while the interior nodes run phase A and phase B; the boundary
-    // nodes' phase B (the only consumer of remote factors) comes last.
-    cudaStream_t c = halo_comm_stream(h);
-    if (!phase(ST_PHASE_A, 1)) return;
-    if (!cuda_ok(cudaEventRecord(halo_event(h, 0), s), "event") ||
-        !cuda_ok(cudaStreamWaitEvent(c, halo_event(h, 0), 0), "wait"))
-        return;
-    if (!halo_exchange(f, h, c)) return;
-    if (!cuda_ok(cudaEventRecord(halo_event(h, 1), c), "event")) return;
-    if (!phase(ST_PHASE_A, 2)) return;
-    *alg_state = 6;
-    if (!phase(ST_PHASE_B, 2)) return;
-    if (!cuda_ok(cudaStreamWaitEvent(s, halo_event(h, 1), 0), "wait")) return;
-    if (!phase(ST_PHASE_B, 1)) return;
-    *alg_state = 10;
+    fused_step(f, h, s, A, *mode, alg_state);
 }
 
 void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimit, int *iter_yn, real_type *dt,
@@ -557,8 +570,19 @@ void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimi
         std::fprintf(stderr, "fesom2-accelerate: vlimit = %d (1, 2 or 3)\n", vl);
         return;
     }
-    if (f->packed || !f->buf[FCT_UV_RHS]) {
-        std::fprintf(stderr, "fesom2-accelerate: the general step runs the stage kernels: padded fields created with UV_rhs\n");
+    if (f->packed) {
+        // the fast path's own layout: fused warp-item phases, phase A in its vlimit variant
+        if (iter) {
+            std::fprintf(stderr, "fesom2-accelerate: the iterative branch runs the stage kernels: padded fields created with UV_rhs\n");
+            return;
+        }
+        Arrays A = arrays_of(f, 1, *dt, *flux_eps, *bignumber);
+        A.vlimit = vl;
+        fused_step(f, h, s, A, 1, alg_state);
+        return;
+    }
+    if (!f->buf[FCT_UV_RHS]) {
+        std::fprintf(stderr, "fesom2-accelerate: the general step runs the stage kernels on padded fields: create them with UV_rhs\n");
         return;
     }
     if (iter && !ensure_iter_buffers(f)) return;

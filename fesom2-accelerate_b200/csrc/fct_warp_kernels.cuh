@@ -455,6 +455,10 @@ __device__ __forceinline__ void wt_next(const Arrays &A, const WtView &V, int la
     if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v, tn);
 }
 
+// VLIMIT_ONE: the vertical 3-point stencil over the cluster bounds (vlimit == 1, reference.cpp:380-392);
+// else A.vlimit is 2 or 3 (docs/refactoring.md:113-148): the cluster bound of a level is widened (2) or
+// narrowed (3) by the node's own a1 maxima of levels z-1 .. z+1, which stand in the staged own row
+template <bool VLIMIT_ONE>
 __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
                                           const double *g_lo, const double *g_v, const WtEarly &E, int raw, int &wn,
                                           WtEarly &En)
@@ -505,13 +509,32 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
     const double nmax = __shfl_down_sync(0xffffffffu, hi0, 1), nmin = __shfl_down_sync(0xffffffffu, lw0, 1);
     if (!I.out) return;
     double bm0 = hi0, bn0 = lw0, bm1 = hi1, bn1 = lw1;
-    if (z0 > 0 && z0 < nz - 1) {
-        bm0 = pick_max(pick_max(pmax, hi0), hi1);
-        bn0 = pick_min(pick_min(pmin, lw0), lw1);
-    }
-    if (z0 + 1 < nz - 1) {
-        bm1 = pick_max(pick_max(hi0, hi1), nmax);
-        bn1 = pick_min(pick_min(lw0, lw1), nmin);
+    if (VLIMIT_ONE) {
+        if (z0 > 0 && z0 < nz - 1) {
+            bm0 = pick_max(pick_max(pmax, hi0), hi1);
+            bn0 = pick_min(pick_min(pmin, lw0), lw1);
+        }
+        if (z0 + 1 < nz - 1) {
+            bm1 = pick_max(pick_max(hi0, hi1), nmax);
+            bn1 = pick_min(pick_min(lw0, lw1), nmin);
+        }
+    } else {
+        // own a1 maxima of levels z0-1 .. z0+2 (the listing takes maxval AND minval from fct_ttf_max)
+        const unsigned char *ar = I.ra + I.own;
+        const double2 a = *reinterpret_cast<const double2 *>(ar);
+        const bool widen = A.vlimit == 2;
+        if (z0 > 0 && z0 < nz - 1) {
+            const double am = *reinterpret_cast<const double *>(ar - 8);
+            const double vmax = pick_max(pick_max(am, a.x), a.y), vmin = pick_min(pick_min(am, a.x), a.y);
+            bm0 = widen ? pick_max(hi0, vmax) : pick_min(hi0, vmax);
+            bn0 = widen ? pick_min(lw0, vmin) : pick_max(lw0, vmin);
+        }
+        if (z0 + 1 < nz - 1) {
+            const double ap = *reinterpret_cast<const double *>(ar + 16);
+            const double vmax = pick_max(pick_max(a.x, a.y), ap), vmin = pick_min(pick_min(a.x, a.y), ap);
+            bm1 = widen ? pick_max(hi1, vmax) : pick_min(hi1, vmax);
+            bn1 = widen ? pick_min(lw1, vmin) : pick_max(lw1, vmin);
+        }
     }
     bm0 -= l0;
     bn0 -= l0;
@@ -623,7 +646,7 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
 // else: b3 vertical + b3 horizontal + c vertical + c horizontal.
 // dynamic smem: WT_SMEM_HEAD + NSTAGE * stage_bytes
 // ------------------------------------------------------------------------------------------------
-template <bool PHASE_A, int NSTAGE, int NWC, int NPW>
+template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true>
 __global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0) + NWC) * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
@@ -821,7 +844,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 WtEarly En;
                 int wn = 0;
                 const int raw = draw(s);
-                if (PHASE_A) wt_item_a(A, V, wi, lane, tn, A.lo + tn, g_v, E, raw, wn, En);
+                if (PHASE_A) wt_item_a<VLIMIT_ONE>(A, V, wi, lane, tn, A.lo + tn, g_v, E, raw, wn, En);
                 else
                     wt_item_b(A, V, wi, lane, tn, g_v, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E, raw,
                               wn, En);

@@ -266,8 +266,10 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
  * executable (src/reference.cpp:51-96 are stubs): *vlimit 1, 2 or 3
  * (md:77-148) and *iter_yn (md:226-290: b3 keeps the rejected part of every flux in FCT_ADF_V2 /
  * FCT_ADF_H2, the limited fluxes update fct_LO, then fct_adf_* = fct_adf_*2 and -- with a halo --
- * the fct_LO halo rows are exchanged for the next pass).  Stage kernels on padded fields created
- * with UV_rhs, in place like mode 0 of fct_ale_step_; *alg_state = 10 on success. */
+ * the fct_LO halo rows are exchanged for the next pass).  Padded fields (created with UV_rhs): stage
+ * kernels, in place like mode 0 of fct_ale_step_.  Packed fields: the fused fast path like mode 1
+ * (limited fluxes in FCT_ADF_*_OUT), phase A in its vlimit variant; the iterative branch is refused
+ * there.  *alg_state = 10 on success. */
 void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimit, int *iter_yn, real_type *dt,
                             real_type *flux_eps, real_type *bignumber, int *alg_state);
 /* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,

@@ -82,6 +82,21 @@ def main():
     # the exchanged halo rows of fct_LO equal their owners' values
     assert np.array_equal(got.fct_LO, want.fct_LO[part.mesh.node_gid]), (rank, "fct_LO halo")
     df.free()
+    # vlimit 2 on the fused fast path (packed fields), overlapped schedule with the halo exchange
+    f = fs[0].copy()
+    f.vlimit = 2
+    want = f.copy()
+    oracle.fct_ale_general(m, want)
+    lf = mesh_mod.slice_fields(f, part)
+    lf.vlimit = 2
+    df = harness.DeviceFields(plan, 1, packed=True)
+    df.upload(lf)
+    assert df.step_general(lf, halo=halo) == 10
+    got = df.download(lf, mode=1)
+    for k in KEYS:
+        assert np.array_equal(getattr(got, k)[:n], getattr(want, k)[g]), (rank, "fused vlimit 2", k)
+    assert np.array_equal(got.fct_adf_h, want.fct_adf_h[part.mesh.edge_gid]), (rank, "fused vlimit 2", "fct_adf_h")
+    df.free()
     dist.barrier()
     halo.free()
     plan.free()

@@ -285,6 +285,27 @@ def test_vlimit_and_iterative_branches(mesh_mod, harness, oracle_mod, name, vlim
     plan.free()
 
 
+@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "deep"])
+@pytest.mark.parametrize("vlimit", [2, 3])
+def test_vlimit_on_the_fused_fast_path(mesh_mod, harness, oracle_mod, name, vlimit):
+    """Packed fields: fct_ale_step_general_ runs the persistent warp-item kernels, phase A in its
+    vlimit 2 / 3 variant (own a1 maxima of levels z-1..z+1 from the staged own row)."""
+    m, f = general_case(mesh_mod, name, vlimit, False)
+    want = f.copy()
+    oracle_mod.fct_ale_general(m, want)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, packed=True)
+    df.upload(f)
+    n0 = harness.abi.launch_count()
+    assert df.step_general(f) == 10
+    assert harness.abi.launch_count() - n0 == 2          # two fused launches
+    check(df.download(f, mode=1), want)
+    f.iter_yn = True
+    assert df.step_general(f) == 0                       # the iterative branch needs padded fields: refused
+    df.free()
+    plan.free()
+
+
 def test_iterative_passes_converge_to_the_plain_limiter_inputs(mesh_mod, harness, oracle_mod):
     """Two passes of the iterative branch followed by the closing non-iterative call (the way
     FESOM2 drives fct_ale with iter_yn), device against oracle."""
