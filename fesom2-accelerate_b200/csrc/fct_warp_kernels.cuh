@@ -214,7 +214,7 @@ __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, co
     asm("{\n"
         ".reg .pred P0, P1, q;\n"
         ".reg .b32 dg, sh, z1;\n"
-        ".reg .f64 s, a, t;\n"
+        ".reg .f64 s, a, t, h0, h1;\n"
         "and.b32 dg, %9, 0xffff;\n"
         "and.b32 sh, %9, 0x80000000;\n"
         "or.b32 sh, sh, 0x3FF00000;\n"
@@ -230,18 +230,23 @@ __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, co
         "selp.f64 %2, %12, %2, q;\n"
         "setp.lt.and.f64 q, %13, %3, P1;\n"
         "selp.f64 %3, %13, %3, q;\n"
-        "abs.f64 a, %14;\n"
-        "fma.rn.f64 t, %14, s, a;\n"
-        "@P0 fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
+        // levels below the edge contribute a flux of +0 (ptxas turns a predicated fp64 accumulate into
+        // DFMA + two FSEL; masking the flux costs one select pair per level instead of two): h = +0
+        // gives t = +0 for the plus sum and -0 or +0 for the minus sum, which change neither
+        "selp.f64 h0, %14, 0d0000000000000000, P0;\n"
+        "selp.f64 h1, %15, 0d0000000000000000, P1;\n"
+        "abs.f64 a, h0;\n"
+        "fma.rn.f64 t, h0, s, a;\n"
+        "fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
         "neg.f64 a, a;\n"
-        "fma.rn.f64 t, %14, s, a;\n"
-        "@P0 fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
-        "abs.f64 a, %15;\n"
-        "fma.rn.f64 t, %15, s, a;\n"
-        "@P1 fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
+        "fma.rn.f64 t, h0, s, a;\n"
+        "fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
+        "abs.f64 a, h1;\n"
+        "fma.rn.f64 t, h1, s, a;\n"
+        "fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
         "neg.f64 a, a;\n"
-        "fma.rn.f64 t, %15, s, a;\n"
-        "@P1 fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
+        "fma.rn.f64 t, h1, s, a;\n"
+        "fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
         "}"
         : "+d"(hi0), "+d"(hi1), "+d"(lw0), "+d"(lw1), "+d"(p0), "+d"(p1), "+d"(m0), "+d"(m1)
         : "r"(z0), "r"(meta), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y), "d"(h.x), "d"(h.y));
@@ -262,28 +267,21 @@ __device__ __forceinline__ void wt_store2(double *p, double a, double b, bool bo
 }
 
 // b1 vertical of two levels (reference.cpp:397-398): p = max(0, f[z]) + max(0, -f[z+1]),
-// m = min(0, f[z]) + min(0, -f[z+1]) with compare-select max / min
+// m = min(0, f[z]) + min(0, -f[z+1]).  On the FP64 pipe, without compares and selects:
+// a = f + |f| = 2 max(0, f) and c = f - |f| = 2 min(0, f) are exact, max(0, -f) = -c / 2 and
+// min(0, -f) = -a / 2, so p = (a_z - c_z+1) / 2 and m = (c_z - a_z+1) / 2 round once, at the same
+// place and to the same value as the sums of the reference (scaling by 2 is exact).  A flux of -0
+// yields m = -0 where the compare-select form yields +0; the sums only feed m*dt*area_inv - eps
+// and further additions, where the two zeros are indistinguishable.
 __device__ __forceinline__ void wt_b1v(double f0, double f1, double f2, double &p0, double &p1, double &m0, double &m1)
 {
-    asm("{\n"
-        ".reg .pred g0, l0, g1, l1, g2, l2;\n"
-        "setp.gt.f64 g0, %4, 0d0000000000000000;\n"
-        "setp.lt.f64 l0, %4, 0d0000000000000000;\n"
-        "setp.gt.f64 g1, %5, 0d0000000000000000;\n"
-        "setp.lt.f64 l1, %5, 0d0000000000000000;\n"
-        "setp.gt.f64 g2, %6, 0d0000000000000000;\n"
-        "setp.lt.f64 l2, %6, 0d0000000000000000;\n"
-        "selp.f64 %0, %4, 0d0000000000000000, g0;\n"
-        "selp.f64 %2, %4, 0d0000000000000000, l0;\n"
-        "selp.f64 %1, %5, 0d0000000000000000, g1;\n"
-        "selp.f64 %3, %5, 0d0000000000000000, l1;\n"
-        "@l1 sub.rn.f64 %0, %0, %5;\n"
-        "@g1 sub.rn.f64 %2, %2, %5;\n"
-        "@l2 sub.rn.f64 %1, %1, %6;\n"
-        "@g2 sub.rn.f64 %3, %3, %6;\n"
-        "}"
-        : "=&d"(p0), "=&d"(p1), "=&d"(m0), "=&d"(m1)
-        : "d"(f0), "d"(f1), "d"(f2));
+    const double a0 = f0 + fabs(f0), c0 = f0 - fabs(f0);
+    const double a1 = f1 + fabs(f1), c1 = f1 - fabs(f1);
+    const double a2 = f2 + fabs(f2), c2 = f2 - fabs(f2);
+    p0 = (a0 - c1) * 0.5;
+    m0 = (c0 - a1) * 0.5;
+    p1 = (a1 - c2) * 0.5;
+    m1 = (c1 - a2) * 0.5;
 }
 
 // One edge of phase B for two levels (docs/refactoring.md:246-261 + :303-314).  n1 = edges[2g],
