@@ -306,6 +306,36 @@ def test_vlimit_on_the_fused_fast_path(mesh_mod, harness, oracle_mod, name, vlim
     plan.free()
 
 
+@pytest.mark.parametrize("knobs", [dict(WT_STAGES=2), dict(WT_STAGES=4, WT_SMEM=50 * 1024), dict(WT_ISSUERS=4), dict(WT_OPT=7)])
+def test_vlimit_fast_path_variants(mesh_mod, harness, abi, oracle_mod, knobs):
+    """The vlimit variant of phase A in its other compiled shapes (ring depth, issuer warps) and
+    with every scheduling option switched on."""
+    m, f = general_case(mesh_mod, "deep", 3, False)
+    want = f.copy()
+    oracle_mod.fct_ale_general(m, want)
+    defaults = dict(WT_STAGES=3, WT_SMEM=0, WT_ISSUERS=0, WT_OPT=2)
+    try:
+        for k, v in knobs.items():
+            abi.tune(k, v)
+        plan = harness.DevicePlan(m)
+        df = harness.DeviceFields(plan, 1, packed=True)
+        df.upload(f)
+        assert df.step_general(f) == 10
+        check(df.download(f, mode=1), want)
+        f1 = f.copy()
+        f1.vlimit = 1
+        want1 = f1.copy()
+        oracle_mod.fct_ale(m, want1)
+        df.upload(f1)
+        assert df.step(f1, mode=1) == 10
+        check(df.download(f1, mode=1), want1)
+        df.free()
+        plan.free()
+    finally:
+        for k, v in defaults.items():
+            abi.tune(k, v)
+
+
 def test_iterative_passes_converge_to_the_plain_limiter_inputs(mesh_mod, harness, oracle_mod):
     """Two passes of the iterative branch followed by the closing non-iterative call (the way
     FESOM2 drives fct_ale with iter_yn), device against oracle."""
