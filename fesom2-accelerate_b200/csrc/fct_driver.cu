@@ -282,7 +282,17 @@ static void build_plan_tiles(Plan *p, const DerivedHost &d, const int *nlev_n)
 }
 
 // ---- warp-item kernels: plan tables, launch ---------------------------------------------------
-static int wt_stages() { return std::min(std::max(env_int("FCT_WT_STAGES", 3), 2), 4); }
+// Ring depth (knob WT_STAGES, 0 / unset: automatic).  Measured, interleaved in thermal steady state
+// (profiles/r1_v14_ab_ring_depth.log): deep columns leave a third of the ring only ~20 nodes per tile,
+// and two larger stages with the copy lists travelling ahead of their blobs (WT_OPT bit 4) beat three
+// stages by 2 % per step on the nl = 70 and nl = 80 meshes, while on nl = 48 (34 nodes per tile)
+// three stages stay ahead by 2 %.  The padded layout cannot send its lists ahead (too many copies).
+static int wt_stages(int nl, bool packed)
+{
+    const int v = env_int("FCT_WT_STAGES", 0);
+    if (v > 0) return std::min(std::max(v, 2), 4);
+    return (packed && nl >= 60) ? 2 : 3;
+}
 // one stage of the ring: an equal share of the 227 KB a CTA may own
 static int wt_stage_cap(int stages) { return ((WT_SMEM_MAX - WT_SMEM_HEAD) / stages) & ~127; }
 
@@ -291,14 +301,14 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
     p->wtiles_ok = false;
     if (env_int("FCT_WTILE", 1) == 0) return;
     const int verbose = env_int("FCT_VERBOSE", 0);
-    int cap = env_int("FCT_WT_SMEM", 0);   // 0: default
-    cap = cap <= 0 ? wt_stage_cap(wt_stages()) : std::min(std::max(cap, 8 * 1024), wt_stage_cap(2));
+    const int cap_knob = env_int("FCT_WT_SMEM", 0);   // 0: default
     int TN = env_int("FCT_WT_NODES", 0);
     TN = TN <= 0 ? 96 : std::min(TN, 255);
     const std::vector<int> *lists[3] = {nullptr, &d.boundary, &d.interior};
     const int nsets = p->H > 0 ? 3 : 1;
     for (int layout = 0; layout < 2; ++layout) {
     const bool packed = layout == 1;
+    const int cap = cap_knob <= 0 ? wt_stage_cap(wt_stages(p->nl, packed)) : std::min(std::max(cap_knob, 8 * 1024), wt_stage_cap(2));
     if (packed) {
         packed_columns(d, nlev_n, p->N + p->H, p->G, p->ncol, p->ecol);
         p->d_ncol = upload_vec(p, p->ncol);
@@ -371,8 +381,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     }
     WarpTilesDev T = packed ? p->wtiles_pk[which] : p->wtiles[which];
     T.diag = env_int("FCT_WT_DIAG", 0);
-    T.opt = env_int("FCT_WT_OPT", 2);   // measured (gpurun_out/s6_sweep_mid.log): 2 is +10 % on phase A, 1 neutral
-    if (T.max_copies > WT_PRE_MAX_COPIES || T.diag != 0) T.opt &= ~4;
+    T.opt = env_int("FCT_WT_OPT", -1);   // < 0: automatic, see below
     if (T.ntiles <= 0) return true;
     if (!packed && (A.pitchL != p->pitch || A.pitchV != p->pitch || A.pitchH != p->pitch)) {
         std::fprintf(stderr, "fesom2-accelerate: the warp-item kernels need the plan's padded pitch\n");
@@ -380,9 +389,13 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     }
     const int stage_bytes = (T.smem_bytes + 127) & ~127;
     // as deep a ring as the tiles of this plan admit
-    int stages = wt_stages();
+    int stages = wt_stages(p->nl, packed);
     while (stages > 2 && WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) --stages;
-    if (stages == 4 && env_int("FCT_WT_STAGES", 3) != 4) stages = 3;
+    // measured (profiles/r1_v11_sched_options_sweep_mid.log, r1_v14_ab_ring_depth.log): first loads before
+    // the rows wait (2) is +10 % on phase A; lists ahead (4) pays with a two-stage ring only; suspended
+    // producers (1) are neutral
+    if (T.opt < 0) T.opt = 2 | (stages == 2 ? 4 : 0);
+    if (T.max_copies > WT_PRE_MAX_COPIES || T.diag != 0) T.opt &= ~4;
     if (WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) {
         std::fprintf(stderr, "fesom2-accelerate: warp tiles of %d B do not fit two stages\n", stage_bytes);
         return false;

@@ -81,7 +81,7 @@ def test_device_resident_step(mesh_mod, harness, oracle_mod, name, mode):
 
 
 @pytest.mark.parametrize("name", ["pi", "deep"])
-@pytest.mark.parametrize("knobs", [dict(WT_STAGES=2), dict(WT_NODES=5), dict(WT_NODES=200, WT_SMEM=110 * 1024),
+@pytest.mark.parametrize("knobs", [dict(WT_STAGES=2), dict(WT_STAGES=3), dict(WT_NODES=5), dict(WT_NODES=200, WT_SMEM=110 * 1024),
                                    dict(WT_WARPS_A=10, WT_WARPS_B=11, WT_ISSUERS=2),
                                    dict(WT_WARPS_A=16, WT_WARPS_B=13, WT_ISSUERS=6, WT_SMEM=20 * 1024)])
 def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, knobs):
@@ -90,7 +90,7 @@ def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, kno
     m, f = cases(mesh_mod, name)
     want = f.copy()
     oracle_mod.fct_ale(m, want)
-    defaults = dict(WT_STAGES=3, WT_NODES=0, WT_SMEM=0, WT_WARPS_A=0, WT_WARPS_B=0, WT_ISSUERS=0)
+    defaults = dict(WT_STAGES=0, WT_NODES=0, WT_SMEM=0, WT_WARPS_A=0, WT_WARPS_B=0, WT_ISSUERS=0)
     try:
         for k, v in knobs.items():
             abi.tune(k, v)
@@ -306,14 +306,14 @@ def test_vlimit_on_the_fused_fast_path(mesh_mod, harness, oracle_mod, name, vlim
     plan.free()
 
 
-@pytest.mark.parametrize("knobs", [dict(WT_STAGES=2), dict(WT_STAGES=4, WT_SMEM=50 * 1024), dict(WT_ISSUERS=4), dict(WT_OPT=7)])
+@pytest.mark.parametrize("knobs", [dict(WT_STAGES=2), dict(WT_STAGES=3), dict(WT_STAGES=4, WT_SMEM=50 * 1024), dict(WT_ISSUERS=4), dict(WT_OPT=7)])
 def test_vlimit_fast_path_variants(mesh_mod, harness, abi, oracle_mod, knobs):
     """The vlimit variant of phase A in its other compiled shapes (ring depth, issuer warps) and
     with every scheduling option switched on."""
     m, f = general_case(mesh_mod, "deep", 3, False)
     want = f.copy()
     oracle_mod.fct_ale_general(m, want)
-    defaults = dict(WT_STAGES=3, WT_SMEM=0, WT_ISSUERS=0, WT_OPT=2)
+    defaults = dict(WT_STAGES=0, WT_SMEM=0, WT_ISSUERS=0, WT_OPT=-1)
     try:
         for k, v in knobs.items():
             abi.tune(k, v)
