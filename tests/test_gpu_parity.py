@@ -454,13 +454,14 @@ def test_step_is_repeatable_and_deterministic(mesh_mod, harness):
     plan.free()
 
 
-@pytest.mark.parametrize("nparts", [2, 5])
-@pytest.mark.parametrize("tiled", [False, True, "warp", "packed"])
-def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled):
+@pytest.mark.parametrize("nparts,tiled,name", [(n, t, "pi") for n in (2, 5) for t in (False, True, "warp", "packed")] +
+                         [(3, "packed", "deep"), (3, "warp", "deep")])
+def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled, name):
     """Every partition of a mesh run on this GPU with the halo exchange emulated through the host:
     owned results of all partitions must reproduce the single-domain oracle bit for bit (boundary /
-    interior node lists and their tiles, halo numbering, cut edges duplicated on both sides)."""
-    m, f = cases(mesh_mod, "pi")
+    interior node lists and their tiles, halo numbering, cut edges duplicated on both sides).  "deep":
+    nl = 80 columns, where the packed layout runs the two-stage ring with the copy lists ahead."""
+    m, f = cases(mesh_mod, name)
     want = f.copy()
     oracle_mod.fct_ale(m, want)
     parts = mesh_mod.partition_mesh(m, nparts)
