@@ -358,15 +358,15 @@ struct WarpVariant {
 #define WT_VB(S, C, I) {k_phase_warp<false, S, C, I>, false, S, C, I}
 static const WarpVariant g_wvariants[] = {
     WT_VA(3, 17, 4), WT_VA(3, 13, 4), WT_VA(3, 15, 6), WT_VA(3, 9, 4), WT_VA(3, 19, 2),
-    WT_VA(2, 17, 4), WT_VA(2, 13, 4), WT_VA(2, 15, 6), WT_VA(4, 17, 4), WT_VA(4, 15, 6),
+    WT_VA(2, 17, 4), WT_VA(2, 13, 4), WT_VA(2, 15, 6), WT_VA(2, 19, 2), WT_VA(4, 17, 4), WT_VA(4, 15, 6),
     WT_VB(3, 19, 4), WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 17, 6), WT_VB(3, 21, 2),
-    WT_VB(2, 19, 4), WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(4, 19, 4), WT_VB(4, 17, 6),
+    WT_VB(2, 19, 4), WT_VB(2, 15, 4), WT_VB(2, 11, 4), WT_VB(2, 21, 2), WT_VB(4, 19, 4), WT_VB(4, 17, 6),
 };
 // phase A with vlimit 2 / 3 (docs/refactoring.md:113-148): the default shapes of the packed and of
 // the padded layout for every ring depth
 #define WT_VL(S, C, I) {k_phase_warp<true, S, C, I, false>, true, S, C, I}
 static const WarpVariant g_wvariants_vl[] = {
-    WT_VL(3, 19, 2), WT_VL(3, 17, 4), WT_VL(2, 17, 4), WT_VL(4, 17, 4),
+    WT_VL(3, 19, 2), WT_VL(3, 17, 4), WT_VL(2, 19, 2), WT_VL(2, 17, 4), WT_VL(4, 17, 4),
 };
 
 

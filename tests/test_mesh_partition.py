@@ -117,3 +117,60 @@ def test_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+@pytest.mark.parametrize("vlimit", [1, 3])
+def test_partitioned_iterative_branch_equals_single_domain(mesh_mod, oracle_mod, vlimit):
+    """N>1 logic of fct_ale_step_general_ on the CPU: per-partition oracle passes with the halo rows of
+    fct_plus / fct_minus exchanged inside a pass and those of fct_LO after an iterative pass (the
+    low-order update touches owned rows only; docs/refactoring.md:265-290) reproduce the single
+    domain bit for bit over an iterative pass followed by the closing plain pass."""
+    m = mesh_mod.make_workload("pi")
+    f = mesh_mod.make_fields(m)
+    f.vlimit = vlimit
+    f.fct_adf_v2, f.fct_adf_h2 = np.zeros_like(f.fct_adf_v), np.zeros_like(f.fct_adf_h)
+    want = f.copy()
+    parts = mesh_mod.partition_mesh(m, 4)
+    lfs = [mesh_mod.slice_fields(f, p) for p in parts]
+
+    def exchange(names):
+        for p, lf in zip(parts, lfs):
+            for peer, nodes in p.send_lists.items():
+                first, cnt = parts[peer].recv_ranges[p.rank]
+                for k in names:
+                    getattr(lfs[peer], k)[first:first + cnt] = getattr(lf, k)[nodes]
+
+    for it in (True, False):
+        want.iter_yn = it
+        oracle_mod.fct_ale_general(m, want)
+        for p, lf in zip(parts, lfs):
+            lf.iter_yn = it
+        # a pass = pre_comm part, exchange of the factors, post part; run the oracle's general
+        # subroutine per partition with the exchange hooked in between
+        pend = []
+        for p, lf in zip(parts, lfs):
+            oracle_mod.a1(p.mesh, lf)
+            oracle_mod.a2(p.mesh, lf)
+            oracle_mod.a3_vlimit(p.mesh, lf)
+            oracle_mod.b1_vertical(p.mesh, lf)
+            oracle_mod.b1_horizontal(p.mesh, lf)
+            oracle_mod.b2(p.mesh, lf)
+        exchange(["fct_plus", "fct_minus"])
+        for p, lf in zip(parts, lfs):
+            if it:
+                oracle_mod.b3_vertical_iter(p.mesh, lf)
+                oracle_mod.b3_horizontal_iter(p.mesh, lf)
+                oracle_mod.lo_update(p.mesh, lf)
+                lf.fct_adf_h[...] = lf.fct_adf_h2
+                lf.fct_adf_v[...] = lf.fct_adf_v2
+            else:
+                oracle_mod.post_comm(p.mesh, lf)
+        if it:
+            exchange(["fct_LO"])
+    for p, lf in zip(parts, lfs):
+        n = p.mesh.myDim_nod2D
+        g = p.mesh.node_gid[:n]
+        for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "fct_LO", "del_ttf_advvert",
+                  "del_ttf_advhoriz"):
+            assert bits_equal(getattr(lf, k)[:n], getattr(want, k)[g]), (p.rank, k)
+        assert bits_equal(lf.fct_adf_h, want.fct_adf_h[p.mesh.edge_gid]), p.rank
