@@ -403,7 +403,9 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // consumer / issuer warps: the closest compiled variant (0: default)
     int nwc = env_int(isA ? "FCT_WT_WARPS_A" : "FCT_WT_WARPS_B", 0), npw = env_int("FCT_WT_ISSUERS", 0);
     // 24 warps in all at 80 registers; the packed layout needs a sixth of the bulk copies: two issuers
-    npw = npw <= 0 ? (packed ? 2 : 4) : npw;
+    // (with the lists ahead the issuers also pull the rows into L2: four again, measured
+    //  profiles/r1_v14_ab_ring_depth.log)
+    npw = npw <= 0 ? ((packed && stages != 2) ? 2 : 4) : npw;
     nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
     constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
