@@ -1,7 +1,10 @@
 // Device-resident path: plan / fields / step (Part 2 of include/fesom2-accelerate.h).
-// Rows are padded to an even pitch so every column starts 16-byte aligned and each thread moves
-// one double2 per array; a step is ten stage launches (mode 0) or two fused launches (mode 1),
-// optionally split into boundary / interior node sets around the NVLink halo exchange.
+// Two storage layouts: padded rows (64-byte pitch: every column starts on a DRAM sector, each thread
+// moves one double2 per array; all kernels) and the packed level storage of the fast path (active
+// levels only, columns back to back; the warp-item kernels).  A step is ten stage launches (mode 0)
+// or two fused launches (modes 1-3), optionally split into boundary / interior node sets around the
+// NVLink halo exchange; fct_ale_step_general_ adds the vlimit 2 / 3 and iterative branches of the
+// subroutine.  Host copies go through one contiguous PCIe copy + a repack kernel.
 #include <cuda_runtime.h>
 
 #include <algorithm>
