@@ -365,6 +365,11 @@ static const WarpVariant g_wvariants[] = {
 // phase A with vlimit 2 / 3 (docs/refactoring.md:113-148): the default shapes of the packed and of
 // the padded layout for every ring depth
 #define WT_VL(S, C, I) {k_phase_warp<true, S, C, I, false>, true, S, C, I}
+// phase B of the iterative branch (docs/refactoring.md:226-290)
+#define WT_IT(S, C, I) {k_phase_warp<false, S, C, I, true, true>, false, S, C, I}
+static const WarpVariant g_wvariants_it[] = {
+    WT_IT(3, 21, 2), WT_IT(3, 19, 4), WT_IT(2, 19, 4), WT_IT(4, 19, 4),
+};
 static const WarpVariant g_wvariants_vl[] = {
     WT_VL(3, 19, 2), WT_VL(3, 17, 4), WT_VL(2, 19, 2), WT_VL(2, 17, 4), WT_VL(4, 17, 4),
 };
@@ -373,8 +378,9 @@ static const WarpVariant g_wvariants_vl[] = {
 // which: 0 all owned nodes, 1 boundary list, 2 interior list
 bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntracers, cudaStream_t s)
 {
-    const bool isA = stage == ST_PHASE_A;
+    const bool isA = stage == ST_PHASE_A, iter = stage == ST_PHASE_B_ITER;
     const bool packed = A.pitchL == 0;   // Arrays of a packed Fields object carry no pitch
+    if (iter && (!A.adf_v2 || !A.adf_h2)) return false;
     if (packed ? !p->wtiles_pk_ok : !p->wtiles_ok) {
         std::fprintf(stderr, "fesom2-accelerate: this plan has no warp-item tiles for this layout\n");
         return false;
@@ -409,11 +415,12 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
     constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
-    constexpr int NV = NV1 + NVL;
+    constexpr int NVI = sizeof(g_wvariants_it) / sizeof(g_wvariants_it[0]);
+    constexpr int NV = NV1 + NVL + NVI;
     const bool vl = isA && A.vlimit != 1 && A.vlimit != 0;
-    const WarpVariant *table = vl ? g_wvariants_vl : g_wvariants;
+    const WarpVariant *table = vl ? g_wvariants_vl : (iter ? g_wvariants_it : g_wvariants);
     int vi = -1, best = 1 << 30;
-    for (int i = 0; i < (vl ? NVL : NV1); ++i) {
+    for (int i = 0; i < (vl ? NVL : (iter ? NVI : NV1)); ++i) {
         if (table[i].stages != stages || table[i].phase_a != isA) continue;
         const int dist = 4 * std::abs(table[i].consumers - nwc) + std::abs(table[i].issuers - npw);
         if (dist < best) {
@@ -425,6 +432,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     const int ph = isA ? 0 : 1;
     const WarpVariant &v = table[vi];
     if (vl) vi += NV1;   // slot in the attribute table below
+    if (iter) vi += NV1 + NVL;
     const size_t smem = WT_SMEM_HEAD + (size_t)stages * stage_bytes;
     static size_t attr_set[2][NV] = {};
     if (smem > attr_set[ph][vi]) {

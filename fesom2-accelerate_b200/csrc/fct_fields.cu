@@ -183,16 +183,17 @@ static bool run_stage(Fields *f, const Arrays &A, int stage, const int *list, in
 
 // The two fused phases of one step (modes 1, 2, 3 of fct_ale_step_), overlapped with the halo exchange
 // when there is one.  A.vlimit selects the a3 variant of the warp-item phase A.
-static void fused_step(Fields *f, Halo *h, cudaStream_t s, const Arrays &A, int mode, int *alg_state)
+static void fused_step(Fields *f, Halo *h, cudaStream_t s, const Arrays &A, int mode, int *alg_state, bool iter = false)
 {
     const Plan *p = f->plan;
     const int N = p->N;
     const bool warped = (f->packed ? p->wtiles_pk_ok : p->wtiles_ok) && mode == 1;
     const bool tiled = p->tiles_ok && (mode == 3 || (mode == 1 && !warped));
-    if (A.vlimit != 1 && !warped) {
-        std::fprintf(stderr, "fesom2-accelerate: vlimit 2 / 3 are fused in the warp-item kernels only\n");
+    if ((A.vlimit != 1 || iter) && !warped) {
+        std::fprintf(stderr, "fesom2-accelerate: vlimit 2 / 3 and the iterative branch are fused in the warp-item kernels only\n");
         return;
     }
+    const int stage_b = iter ? ST_PHASE_B_ITER : ST_PHASE_B;
     // one fused phase over a node set: 0 all owned, 1 boundary, 2 interior
     auto phase = [&](int stage, int which) -> bool {
         if (warped) return launch_warp(stage, A, p, which, f->T, s);
@@ -204,7 +205,7 @@ static void fused_step(Fields *f, Halo *h, cudaStream_t s, const Arrays &A, int 
     if (!h) {
         if (!phase(ST_PHASE_A, 0)) return;
         *alg_state = 6;
-        if (!phase(ST_PHASE_B, 0)) return;
+        if (!phase(stage_b, 0)) return;
         *alg_state = 10;
         return;
     }
@@ -220,9 +221,9 @@ static void fused_step(Fields *f, Halo *h, cudaStream_t s, const Arrays &A, int 
     if (!cuda_ok(cudaEventRecord(halo_event(h, 1), c), "event")) return;
     if (!phase(ST_PHASE_A, 2)) return;
     *alg_state = 6;
-    if (!phase(ST_PHASE_B, 2)) return;
+    if (!phase(stage_b, 2)) return;
     if (!cuda_ok(cudaStreamWaitEvent(s, halo_event(h, 1), 0), "wait")) return;
-    if (!phase(ST_PHASE_B, 1)) return;
+    if (!phase(stage_b, 1)) return;
     *alg_state = 10;
 }
 
@@ -292,6 +293,8 @@ static bool ensure_iter_buffers(Fields *f)
         if (!cuda_ok(cudaMalloc(&f->buf[id], n * sizeof(double)), "cudaMalloc(iter buffers)") ||
             !cuda_ok(cudaMemset(f->buf[id], 0, n * sizeof(double)), "cudaMemset(iter buffers)"))
             return false;
+        // the caller's streams are non-blocking: they do not wait for the null stream's memset
+        if (!cuda_ok(cudaStreamSynchronize(0), "cudaMemset(iter buffers)")) return false;
     }
     return true;
 }
@@ -324,6 +327,8 @@ static void fields_create(void **fields, void **plan, int *ntracers, bool with_u
         ok = cuda_ok(cudaMalloc(&f->buf[id], n * sizeof(double)), "cudaMalloc(fields)") &&
              cuda_ok(cudaMemset(f->buf[id], 0, n * sizeof(double)), "cudaMemset(fields)");
     }
+    // the callers' streams are non-blocking: make sure no memset of the null stream is still pending
+    ok = ok && cuda_ok(cudaStreamSynchronize(0), "cudaMemset(fields)");
     if (!ok) {
         for (double *b : f->buf)
             if (b) cudaFree(b);
@@ -362,7 +367,7 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
 {
     *istat = 1;
     Fields *f = F_(fields);
-    if (f && (*field == FCT_ADF_V2 || *field == FCT_ADF_H2) && !f->packed && !ensure_iter_buffers(f)) return;
+    if (f && (*field == FCT_ADF_V2 || *field == FCT_ADF_H2) && !ensure_iter_buffers(f)) return;
     if (!f || *field < 0 || *field >= FCT_FIELD_COUNT || !f->buf[*field] || !host) return;
     const FieldMeta m = meta_of(*field);
     const int t = m.per_tracer ? *tracer : 0;
@@ -575,13 +580,20 @@ void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimi
     }
     if (f->packed) {
         // the fast path's own layout: fused warp-item phases, phase A in its vlimit variant
-        if (iter) {
-            std::fprintf(stderr, "fesom2-accelerate: the iterative branch runs the stage kernels: padded fields created with UV_rhs\n");
-            return;
-        }
+        if (iter && !ensure_iter_buffers(f)) return;
         Arrays A = arrays_of(f, 1, *dt, *flux_eps, *bignumber);
         A.vlimit = vl;
-        fused_step(f, h, s, A, 1, alg_state);
+        fused_step(f, h, s, A, 1, alg_state, iter);
+        if (!iter || *alg_state != 10) return;
+        // fct_adf_* = fct_adf_*2 (md:288-289), then the fct_LO halo rows for the next pass
+        *alg_state = 9;
+        if (!cuda_ok(cudaMemcpyAsync(f->buf[FCT_ADF_V], f->buf[FCT_ADF_V2], field_doubles(f, FCT_ADF_V) * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, s), "fct_adf_v = fct_adf_v2") ||
+            !cuda_ok(cudaMemcpyAsync(f->buf[FCT_ADF_H], f->buf[FCT_ADF_H2], field_doubles(f, FCT_ADF_H) * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, s), "fct_adf_h = fct_adf_h2"))
+            return;
+        if (h && !halo_exchange_field(f, h, s, FCT_LO)) return;
+        *alg_state = 10;
         return;
     }
     if (!f->buf[FCT_UV_RHS]) {

@@ -13,7 +13,8 @@ enum Stage {
     ST_PHASE_A_WARP = 18, ST_PHASE_B_WARP = 19,
     ST_B1H_ATOMIC = 24, ST_CH_ATOMIC = 25,   // measured alternatives (fp64 atomics), never on the product path
     // vlimit 2 / 3 and the iterative branch (docs/refactoring.md:113-148, :226-290)
-    ST_A3_VLIMIT2 = 26, ST_A3_VLIMIT3 = 27, ST_B3V_ITER = 28, ST_B3H_ITER = 29, ST_LO_UPDATE = 30, ST_LAST = 30
+    ST_A3_VLIMIT2 = 26, ST_A3_VLIMIT3 = 27, ST_B3V_ITER = 28, ST_B3H_ITER = 29, ST_LO_UPDATE = 30, ST_LAST = 30,
+    ST_PHASE_B_ITER = 31   // internal: the warp-item phase B of the iterative branch (launch_warp only)
 };
 
 bool cuda_ok(cudaError_t e, const char *what);

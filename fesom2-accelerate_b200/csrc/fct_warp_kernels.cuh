@@ -407,7 +407,7 @@ __device__ __forceinline__ WtItem wt_item(const WtView &V, int wi, int lane)
 struct WtEarly {
     double f0, f1, f2, a0, a1;
 };
-template <bool PHASE_A>
+template <bool PHASE_A, bool ITER = false>
 __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, int wi, int lane, const double *g_v, size_t tn)
 {
     WtEarly E;
@@ -428,7 +428,7 @@ __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, in
             E.a1 = aa.y;
             // the operands of c vertical are consumed after the item's edge loop: pull them into L2
             // now (one probe per 64 bytes) instead of holding 24 registers for loads in flight
-            if ((z0 & 7) == 0) {
+            if (!ITER && (z0 & 7) == 0) {
                 prefetch_l2(A.del_v + tn + grow);
                 prefetch_l2(A.del_h + tn + grow);
                 prefetch_l2(A.ttf + tn + grow);
@@ -445,12 +445,12 @@ __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, in
 // What an item does for its successor right before its edge loop: broadcast the index lane 0 drew
 // at the top of the item (the shared atomic has long returned) and issue the successor's
 // first-needed loads, which then have the edge loop and the epilogue to arrive.
-template <bool PHASE_A>
+template <bool PHASE_A, bool ITER = false>
 __device__ __forceinline__ void wt_next(const Arrays &A, const WtView &V, int lane, size_t tn, const double *g_v,
                                         int raw, int &wn, WtEarly &En)
 {
     wn = __shfl_sync(0xffffffffu, raw, 0);
-    if (wn < V.n_witems) En = wt_early<PHASE_A>(A, V, wn, lane, g_v, tn);
+    if (wn < V.n_witems) En = wt_early<PHASE_A, ITER>(A, V, wn, lane, g_v, tn);
 }
 
 // VLIMIT_ONE: the vertical 3-point stencil over the cluster bounds (vlimit == 1, reference.cpp:380-392);
@@ -639,12 +639,127 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
     wt_store2(A.del_h + off, dh0, dh1, both);
 }
 
+
+// a / b exactly as IEEE division; a zero numerator (a fully rejected or absent flux) takes the
+// branch-free detour of limit_quotient instead of the division's slow path
+__device__ __forceinline__ double div_exact(double a, double b)
+{
+    const bool z = a == 0.;
+    const double q = (z ? 1. : a) / b;
+    return z ? a * q : q;
+}
+
+// ---- phase B of the iterative branch (iter_yn, docs/refactoring.md:226-290): one warp item ----------
+// b3 vertical + b3 horizontal as in wt_item_b, but what leaves the item is the REJECTED part of every
+// flux, (1-ae)*flux, into fct_adf_v2 / fct_adf_h2 (md:228-230, :258-260), and the low-order solution
+// updated with the limited parts (md:265-287: the vertical term, then the node's edges in ascending
+// id; x*dt/area/hnode_new evaluated left to right).  The limited fluxes themselves are not stored:
+// the subroutine ends with fct_adf_* = fct_adf_*2.
+__device__ __forceinline__ void wt_item_b_iter(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
+                                               const double *g_v, double *g_v2, double *g_h2, const WtEarly &E, int raw,
+                                               int &wn, WtEarly &En)
+{
+    const WtItem I = wt_item(V, wi, lane);
+    wt_next<false, true>(A, V, lane, tn, g_v, raw, wn, En);
+    if (!I.out) return;
+    const int z0 = I.z0, nz = I.nz;
+    const size_t off = tn + I.grow;
+    double *lo = const_cast<double *>(A.lo) + off;
+    const double2 q_l = *reinterpret_cast<const double2 *>(lo);
+    const double2 q_hw = __ldg(reinterpret_cast<const double2 *>(A.hnode_new + I.grow));
+    const unsigned char *pr = I.ra + I.own, *mr = I.rb + I.own;
+    const double2 pp = *reinterpret_cast<const double2 *>(pr);
+    const double2 mm = *reinterpret_cast<const double2 *>(mr);
+    const double p_m1 = *reinterpret_cast<const double *>(pr - 8);
+    const double m_m1 = *reinterpret_cast<const double *>(mr - 8);
+    const double p_p2 = *reinterpret_cast<const double *>(pr + 16);
+    const double m_p2 = *reinterpret_cast<const double *>(mr + 16);
+    // ---- b3 vertical: factors of levels z0, z0+1 and (for the difference of level z0+1) z0+2 ----
+    double ae0 = 1., ae1 = 1., ae2 = 1.;
+    if (z0 == 0) {
+        ae0 = pick_min(ae0, (E.f0 >= 0.) ? pp.x : mm.x);
+    } else if (E.f0 >= 0.) {
+        ae0 = pick_min(ae0, m_m1);
+        ae0 = pick_min(ae0, pp.x);
+    } else {
+        ae0 = pick_min(ae0, p_m1);
+        ae0 = pick_min(ae0, mm.x);
+    }
+    const bool in1 = z0 + 1 < nz, in2 = z0 + 2 < nz;
+    if (in1) {
+        if (E.f1 >= 0.) {
+            ae1 = pick_min(ae1, mm.x);
+            ae1 = pick_min(ae1, pp.y);
+        } else {
+            ae1 = pick_min(ae1, pp.x);
+            ae1 = pick_min(ae1, mm.y);
+        }
+    }
+    if (in2) {
+        if (E.f2 >= 0.) {
+            ae2 = pick_min(ae2, mm.y);
+            ae2 = pick_min(ae2, p_p2);
+        } else {
+            ae2 = pick_min(ae2, pp.y);
+            ae2 = pick_min(ae2, m_p2);
+        }
+    }
+    const double fl0 = ae0 * E.f0, fl1 = in1 ? ae1 * E.f1 : E.f1, fl2 = in2 ? ae2 * E.f2 : E.f2;
+    if (z0 > 0) g_v2[I.grow] = (1.0 - ae0) * E.f0;
+    if (in1) g_v2[I.grow + 1] = (1.0 - ae1) * E.f1;
+    // ---- low-order update, vertical term ----
+    double l0 = q_l.x + div_exact(div_exact((fl0 - fl1) * A.dt, E.a0), q_hw.x);
+    double l1 = q_l.y + div_exact(div_exact((fl1 - fl2) * A.dt, E.a1), q_hw.y);
+    // ---- b3 horizontal + low-order update over the node's edges, ascending edge id ----
+    for (int k = 0; k < I.cnt; ++k) {
+        const int4 e = I.en[k];
+        const double2 po = *reinterpret_cast<const double2 *>(I.ra + e.y);
+        const double2 mo = *reinterpret_cast<const double2 *>(I.rb + e.y);
+        const double2 h = *reinterpret_cast<const double2 *>(I.re + e.x);
+        const int dg = e.z & 0xffff;
+        const bool second = e.z < 0, writer = e.z & 0x40000000;
+        double rj0 = 0., rj1 = 0.;
+        if (z0 < dg) {
+            const double p1 = second ? po.x : pp.x, m1 = second ? mo.x : mm.x;
+            const double p2 = second ? pp.x : po.x, m2 = second ? mm.x : mo.x;
+            double ae = 1.;
+            if (h.x >= 0.) {
+                ae = pick_min(ae, p1);
+                ae = pick_min(ae, m2);
+            } else {
+                ae = pick_min(ae, m1);
+                ae = pick_min(ae, p2);
+            }
+            rj0 = (1.0 - ae) * h.x;
+            const double x = div_exact(div_exact(ae * h.x * A.dt, E.a0), q_hw.x);
+            l0 = second ? l0 - x : l0 + x;
+        }
+        if (z0 + 1 < dg) {
+            const double p1 = second ? po.y : pp.y, m1 = second ? mo.y : mm.y;
+            const double p2 = second ? pp.y : po.y, m2 = second ? mm.y : mo.y;
+            double ae = 1.;
+            if (h.y >= 0.) {
+                ae = pick_min(ae, p1);
+                ae = pick_min(ae, m2);
+            } else {
+                ae = pick_min(ae, m1);
+                ae = pick_min(ae, p2);
+            }
+            rj1 = (1.0 - ae) * h.y;
+            const double x = div_exact(div_exact(ae * h.y * A.dt, E.a1), q_hw.y);
+            l1 = second ? l1 - x : l1 + x;
+        }
+        if (writer && z0 < dg) wt_store2(g_h2 + (unsigned)e.w + z0, rj0, rj1, z0 + 1 < dg);
+    }
+    wt_store2(lo, l0, l1, in1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // The persistent kernel.  PHASE_A: a1 + a2 + a3 + b1 vertical + b1 horizontal + b2;
 // else: b3 vertical + b3 horizontal + c vertical + c horizontal.
 // dynamic smem: WT_SMEM_HEAD + NSTAGE * stage_bytes
 // ------------------------------------------------------------------------------------------------
-template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true>
+template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false>
 __global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0) + NWC) * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
@@ -836,13 +951,15 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             // warp waits for the tile's rows
             int wi = __shfl_sync(0xffffffffu, draw(s), 0);
             WtEarly E;
-            if (wi < V.n_witems) E = wt_early<PHASE_A>(A, V, wi, lane, g_v, tn);
+            if (wi < V.n_witems) E = wt_early<PHASE_A, ITER>(A, V, wi, lane, g_v, tn);
             if (first_loads_ahead) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             while (wi < V.n_witems) {
                 WtEarly En;
                 int wn = 0;
                 const int raw = draw(s);
                 if (PHASE_A) wt_item_a<VLIMIT_ONE>(A, V, wi, lane, tn, A.lo + tn, g_v, E, raw, wn, En);
+                else if (ITER)
+                    wt_item_b_iter(A, V, wi, lane, tn, g_v, A.adf_v2 + tr * A.ts_nodev, A.adf_h2 + tr * A.ts_edge, E, raw, wn, En);
                 else
                     wt_item_b(A, V, wi, lane, tn, g_v, A.adf_v_out + tr * A.ts_nodev, A.adf_h_out + tr * A.ts_edge, E, raw,
                               wn, En);

@@ -227,8 +227,8 @@ enum fct_field_id {
     FCT_HNODE = 6, FCT_HNODE_NEW = 7, FCT_DEL_V = 8, FCT_DEL_H = 9, FCT_TTF_MAX = 10,
     FCT_TTF_MIN = 11, FCT_PLUS = 12, FCT_MINUS = 13, FCT_UV_RHS = 14, FCT_ADF_H_OUT = 15,
     FCT_ADF_V_OUT = 16,
-    /* rejected flux parts of the iterative branch (docs/refactoring.md:228-230, :258-260), padded
-     * fields only, allocated at first use */
+    /* rejected flux parts of the iterative branch (docs/refactoring.md:228-230, :258-260),
+     * allocated at first use */
     FCT_ADF_V2 = 17, FCT_ADF_H2 = 18, FCT_FIELD_COUNT = 19
 };
 /* dense host array (the Fortran layout above) <-> padded device rows of tracer *tracer
@@ -267,9 +267,9 @@ void fct_ale_step_(void **fields, void **halo, void **stream, int *mode, real_ty
  * (md:77-148) and *iter_yn (md:226-290: b3 keeps the rejected part of every flux in FCT_ADF_V2 /
  * FCT_ADF_H2, the limited fluxes update fct_LO, then fct_adf_* = fct_adf_*2 and -- with a halo --
  * the fct_LO halo rows are exchanged for the next pass).  Padded fields (created with UV_rhs): stage
- * kernels, in place like mode 0 of fct_ale_step_.  Packed fields: the fused fast path like mode 1
- * (limited fluxes in FCT_ADF_*_OUT), phase A in its vlimit variant; the iterative branch is refused
- * there.  *alg_state = 10 on success. */
+ * kernels, in place like mode 0 of fct_ale_step_.  Packed fields: the fused fast path, two launches
+ * like mode 1 (plain pass: limited fluxes in FCT_ADF_*_OUT), phase A in its vlimit variant and, for
+ * an iterative pass, phase B in its iterative variant.  *alg_state = 10 on success. */
 void fct_ale_step_general_(void **fields, void **halo, void **stream, int *vlimit, int *iter_yn, real_type *dt,
                             real_type *flux_eps, real_type *bignumber, int *alg_state);
 /* single stage of the staged mode (per-stage ncu sweep): 0 a1, 1 a2, 2 a3, 3 b1v, 4 b1h, 5 b2,

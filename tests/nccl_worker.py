@@ -97,6 +97,23 @@ def main():
         assert np.array_equal(getattr(got, k)[:n], getattr(want, k)[g]), (rank, "fused vlimit 2", k)
     assert np.array_equal(got.fct_adf_h, want.fct_adf_h[part.mesh.edge_gid]), (rank, "fused vlimit 2", "fct_adf_h")
     df.free()
+    # the iterative branch on the fused fast path: one iterative pass (fct_LO halo exchanged), one plain
+    f = fs[0].copy()
+    f.vlimit, f.iter_yn = 1, True
+    f.fct_adf_v2, f.fct_adf_h2 = np.zeros_like(f.fct_adf_v), np.zeros_like(f.fct_adf_h)
+    want = f.copy()
+    lf = mesh_mod.slice_fields(f, part)
+    df = harness.DeviceFields(plan, 1, packed=True)
+    df.upload(lf)
+    for it in (True, False):
+        want.iter_yn = lf.iter_yn = it
+        oracle.fct_ale_general(m, want)
+        assert df.step_general(lf, halo=halo) == 10
+    got = df.download(lf, mode=1)
+    act = np.arange(m.L)[None, :] < (part.mesh.nlevels_nod2D[:n, None] - 1)
+    for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz"):
+        assert np.array_equal(getattr(got, k)[:n][act], getattr(want, k)[g][act]), (rank, "fused iter", k)
+    df.free()
     dist.barrier()
     halo.free()
     plan.free()

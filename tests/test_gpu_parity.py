@@ -300,8 +300,52 @@ def test_vlimit_on_the_fused_fast_path(mesh_mod, harness, oracle_mod, name, vlim
     assert df.step_general(f) == 10
     assert harness.abi.launch_count() - n0 == 2          # two fused launches
     check(df.download(f, mode=1), want)
-    f.iter_yn = True
-    assert df.step_general(f) == 0                       # the iterative branch needs padded fields: refused
+    df.free()
+    plan.free()
+
+
+@pytest.mark.parametrize("name", ["tiny", "pi", "deep"])
+@pytest.mark.parametrize("vlimit", [1, 3])
+def test_iterative_branch_on_the_fused_fast_path(mesh_mod, harness, oracle_mod, name, vlimit):
+    """Packed fields, iter_yn: phase A + the iterative variant of the warp-item phase B (rejected flux
+    parts to fct_adf_*2, low-order update with exact divisions in the listing's order), then
+    fct_adf_* = fct_adf_*2; two iterative passes and the closing plain pass, against the oracle.
+    Cells without a slot in the packed storage are not the device's: compared on the slots."""
+    m, f = general_case(mesh_mod, name, vlimit, True)
+    want = f.copy()
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, packed=True)
+    df.upload(f)
+    df.upload_field("fct_adf_v2", f.fct_adf_v2)
+    df.upload_field("fct_adf_h2", f.fct_adf_h2)
+    nslot, eslot = df._nslot, df._eslot[:, :m.L]
+
+    def compare(names, got):
+        for k in names:
+            a, b = getattr(got, k), getattr(want, k)
+            mask = eslot if k.startswith("fct_adf_h") else nslot[:, :a.shape[1]]
+            assert bits_equal(a[mask], b[mask]), f"{k}: {rel_err(a[mask], b[mask], 1e-30):.3e}"
+
+    it_names = ["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "fct_adf_h", "fct_LO",
+                "fct_adf_v2", "fct_adf_h2", "del_ttf_advvert", "del_ttf_advhoriz"]
+    for it in (True, True):
+        want.iter_yn = f.iter_yn = it
+        oracle_mod.fct_ale_general(m, want)
+        n0 = harness.abi.launch_count()
+        assert df.step_general(f) == 10
+        assert harness.abi.launch_count() - n0 == 2          # two fused launches (+ two device copies)
+        compare(it_names, df.download(f, names=it_names))
+    want.iter_yn = f.iter_yn = False
+    oracle_mod.fct_ale_general(m, want)
+    assert df.step_general(f) == 10
+    got = df.download(f, mode=1)
+    compare(["fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "del_ttf_advvert", "del_ttf_advhoriz"], got)
+    # a plain fused pass leaves its limited fluxes in FCT_ADF_V_OUT / FCT_ADF_H_OUT for the active levels
+    # (the bottom flux is not limited, docs/refactoring.md:232, and stays in fct_adf_v)
+    act = np.arange(m.nl)[None, :] < (m.nlevels_nod2D[:, None] - 1)
+    assert bits_equal(got.fct_adf_v[act], want.fct_adf_v[act])
+    eact = np.arange(m.L)[None, :] < m.edge_depth()[:, None]
+    assert bits_equal(got.fct_adf_h[eact], want.fct_adf_h[eact])
     df.free()
     plan.free()
 
