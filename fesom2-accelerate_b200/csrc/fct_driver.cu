@@ -467,8 +467,10 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         cudaGetDevice(&dev_id);
         int *&ring = ctr_rings[dev_id];
         if (!ring) {
+            // (the launch streams are non-blocking: wait for the null stream's memset once)
             if (!cuda_ok(cudaMalloc(&ring, CTR_SLOTS * 2 * sizeof(int)), "cudaMalloc(counters)") ||
-                !cuda_ok(cudaMemset(ring, 0, CTR_SLOTS * 2 * sizeof(int)), "cudaMemset(counters)")) {
+                !cuda_ok(cudaMemset(ring, 0, CTR_SLOTS * 2 * sizeof(int)), "cudaMemset(counters)") ||
+                !cuda_ok(cudaStreamSynchronize(0), "cudaMemset(counters)")) {
                 ring = nullptr;
                 return false;
             }
