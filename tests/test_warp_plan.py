@@ -329,6 +329,27 @@ def test_tables_reproduce_the_oracle(mesh_mod, abi, oracle_mod, name, tn, cap):
     compare(m, f, g, P, want)
 
 
+TWO_STAGE_CAP = ((227 * 1024 - 256 - 4 * 1024) // 2) & ~127     # one stage of the two-stage ring (fct_driver.cu)
+
+
+def test_two_stage_tiles_of_deep_columns(mesh_mod, abi, oracle_mod):
+    """nl = 80 columns in the tiles of the two-stage ring (the default for deep packed meshes): larger
+    tiles, still exact, and every copy list fits the 1 KB slot that travels ahead of its blob
+    (WT_PRE_MAX_COPIES = 120 in fct_warp_kernels.cuh)."""
+    m = mesh_mod.make_mesh(48, 37, 80, seed=3)
+    f = mesh_mod.make_fields(m, seed=4)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    st3, nt3, _, _, _ = inspect(abi, m, 96, 74 * 1024, packed=1)
+    st, nt, smem, blob, off = inspect(abi, m, 96, TWO_STAGE_CAP, packed=1)
+    assert st == 0 and st3 == 0 and smem <= TWO_STAGE_CAP and nt < 0.8 * nt3
+    pk = Packed(m)
+    g, P = emulate(m, f, blob, off, nt, packed=pk)
+    compare_packed(m, f, g, pk, want)
+    P = (m.nl + 7) & ~7
+    assert max(Tile(blob[off[t] * 4: off[t + 1] * 4], P).n_copies for t in range(nt)) <= 120
+
+
 @pytest.mark.parametrize("name,tn,cap", [("tiny", 64, 74 * 1024), ("pi", 96, 74 * 1024), ("pi", 7, 30 * 1024)])
 def test_packed_level_storage(mesh_mod, abi, oracle_mod, name, tn, cap):
     """Columns back to back (active levels only): the tile's own columns and its edge rows in ascending
