@@ -109,8 +109,10 @@ class Packed:
         return out
 
 
-def emulate(m, f, blob, off, ntiles, packed=None):
-    """Both fused phases on the padded (or packed) layout; returns the dict of device-layout result arrays."""
+def emulate(m, f, blob, off, ntiles, packed=None, vlimit=1):
+    """Both fused phases on the padded (or packed) layout; returns the dict of device-layout result arrays.
+    vlimit 2 / 3: the variant of phase A that reads the own a1 maxima of levels z-1..z+1 from the
+    staged own row (wt_item_a<false> in fct_warp_kernels.cuh)."""
     P = (m.nl + 7) & ~7
     L = m.L
     names = ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area", "area_inv", "hnode", "hnode_new", "del_ttf_advvert",
@@ -161,7 +163,7 @@ def emulate(m, f, blob, off, ntiles, packed=None):
                         q = lanes[vl + 1] if vl + 1 < W else None
                         assert q is not None and q["ln"] == s["ln"] and q["z0"] == s["z0"] + 2
                 if phase == "A":
-                    phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big)
+                    phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big, vlimit)
                 else:
                     phase_b_item(T, lanes, RA, RB, RE, g, dt)
             if phase == "A":
@@ -172,7 +174,7 @@ def emulate(m, f, blob, off, ntiles, packed=None):
     return g, P
 
 
-def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
+def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big, vlimit=1):
     tv = []
     for s in lanes:
         if s is None:
@@ -213,7 +215,14 @@ def phase_a_item(T, lanes, RA, RB, RE, g, dt, eps, big):
             if z >= nz:
                 continue
             x, y = s["hi"][v], s["lw"][v]
-            if 0 < z < nz - 1:
+            if vlimit != 1:
+                if 0 < z < nz - 1:
+                    own = [RA[s["own"] + z + d] for d in (-1, 0, 1)]
+                    assert not any(np.isnan(a) for a in own), "own row level that was never staged"
+                    vmax = pmax(pmax(own[0], own[1]), own[2])
+                    vmin = pmin(pmin(own[0], own[1]), own[2])
+                    x, y = (pmax(x, vmax), pmin(y, vmin)) if vlimit == 2 else (pmin(x, vmax), pmax(y, vmin))
+            elif 0 < z < nz - 1:
                 if v == 0:
                     pv = tv[vl - 1]
                     x = pmax(pmax(pv["hi"][1], x), s["hi"][1])
@@ -327,6 +336,43 @@ def test_tables_reproduce_the_oracle(mesh_mod, abi, oracle_mod, name, tn, cap):
     assert st == 0 and nt >= 1 and smem <= cap
     g, P = emulate(m, f, blob, off, nt)
     compare(m, f, g, P, want)
+
+
+@pytest.mark.parametrize("vlimit", [2, 3])
+@pytest.mark.parametrize("packed", [0, 1])
+def test_tables_serve_the_vlimit_variant(mesh_mod, abi, oracle_mod, vlimit, packed):
+    """vlimit 2 / 3 on the fused path need nothing the tables do not already stage: the own row holds
+    every level the vertical neighbourhood reads (docs/refactoring.md:113-148)."""
+    m = mesh_mod.make_workload("pi")
+    f = mesh_mod.make_fields(m)
+    f.vlimit = vlimit
+    want = f.copy()
+    oracle_mod.fct_ale_general(m, want)
+    st, nt, smem, blob, off = inspect(abi, m, 96, 74 * 1024, packed=packed)
+    assert st == 0
+    if packed:
+        pk = Packed(m)
+        g, P = emulate(m, f, blob, off, nt, packed=pk, vlimit=vlimit)
+        compare_packed(m, f, g, pk, want)
+    else:
+        g, P = emulate(m, f, blob, off, nt, vlimit=vlimit)
+        compare(m, f, g, P, want)
+
+
+@pytest.mark.parametrize("nx,ny,nl,seed,tn,cap", [(23, 17, 13, 5, 11, 20 * 1024), (31, 9, 30, 6, 64, 74 * 1024),
+                                                  (12, 40, 6, 7, 200, 111 * 1024)])
+def test_random_meshes_packed(mesh_mod, abi, oracle_mod, nx, ny, nl, seed, tn, cap):
+    """Other shapes of the generator (aspect ratios, depths from 6 to 30 levels, land masks of other
+    seeds) through the packed tables at three tile sizes."""
+    m = mesh_mod.make_mesh(nx, ny, nl, seed=seed)
+    f = mesh_mod.make_fields(m, seed=seed + 1)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    st, nt, smem, blob, off = inspect(abi, m, tn, cap, packed=1)
+    assert st == 0 and smem <= cap
+    pk = Packed(m)
+    g, P = emulate(m, f, blob, off, nt, packed=pk)
+    compare_packed(m, f, g, pk, want)
 
 
 TWO_STAGE_CAP = ((227 * 1024 - 256 - 4 * 1024) // 2) & ~127     # one stage of the two-stage ring (fct_driver.cu)
