@@ -195,6 +195,8 @@ static bool upload_derived(Plan *p, const DerivedHost &d)
     p->dev.edg = upload_vec(p, d.edg);
     p->d_boundary = upload_vec(p, d.boundary);
     p->d_interior = upload_vec(p, d.interior);
+    p->boundary_flag.assign((size_t)p->N, 0);
+    for (int n : d.boundary) p->boundary_flag[(size_t)n] = 1;
     p->n_boundary = (int)d.boundary.size();
     p->n_interior = (int)d.interior.size();
     return p->dev.nbr_off && p->dev.nbr && p->dev.fillmin && p->dev.edg_off && p->dev.edg &&
@@ -310,7 +312,13 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
     const bool packed = layout == 1;
     const int cap = cap_knob <= 0 ? wt_stage_cap(wt_stages(p->nl, packed)) : std::min(std::max(cap_knob, 8 * 1024), wt_stage_cap(2));
     if (packed) {
-        packed_columns(d, nlev_n, p->N + p->H, p->G, p->ncol, p->ecol);
+        if (!packed_columns(d, nlev_n, p->N + p->H, p->G, p->ncol, p->ecol)) {
+            // fct_ale_fields_create_packed_ then answers istat = 1; the padded layout stays available
+            std::fprintf(stderr, "fesom2-accelerate: packed column offsets of this mesh exceed 32 bits: no packed level storage\n");
+            p->ncol.clear();
+            p->ecol.clear();
+            return;
+        }
         p->d_ncol = upload_vec(p, p->ncol);
         p->d_ecol = upload_vec(p, p->ecol);
         if (!p->d_ncol || !p->d_ecol) return;
@@ -345,6 +353,40 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
     if (packed) p->wtiles_pk_ok = true;
     else p->wtiles_ok = true;
     }
+}
+
+// Per-DEVICE launch state (a process may drive several GPUs): the opt-in to > 48 KB of dynamic shared
+// memory is a per-device function attribute, and so are the SM count and the occupancy.
+static std::mutex g_dev_mutex;
+static int current_device()
+{
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    return dev_id;
+}
+static bool ensure_smem_attr(const void *fn, size_t smem, bool *first = nullptr)
+{
+    static std::map<std::pair<int, const void *>, size_t> done;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    size_t &have = done[std::make_pair(current_device(), fn)];
+    if (first) *first = false;
+    if (smem <= have) return true;
+    if (!cuda_ok(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute")) return false;
+    have = smem;
+    if (first) *first = true;
+    return true;
+}
+static int device_sms()
+{
+    static std::map<int, int> sms;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    const int dev_id = current_device();
+    int &n = sms[dev_id];
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev_id);
+        n = std::max(n, 1);
+    }
+    return n;
 }
 
 typedef void (*warp_kern_t)(Arrays, WarpTilesDev, int, int, int *);
@@ -416,7 +458,6 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
     constexpr int NVI = sizeof(g_wvariants_it) / sizeof(g_wvariants_it[0]);
-    constexpr int NV = NV1 + NVL + NVI;
     const bool vl = isA && A.vlimit != 1 && A.vlimit != 0;
     const WarpVariant *table = vl ? g_wvariants_vl : (iter ? g_wvariants_it : g_wvariants);
     int vi = -1, best = 1 << 30;
@@ -429,27 +470,14 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         }
     }
     if (vi < 0) return false;
-    const int ph = isA ? 0 : 1;
     const WarpVariant &v = table[vi];
-    if (vl) vi += NV1;   // slot in the attribute table below
-    if (iter) vi += NV1 + NVL;
     const size_t smem = WT_SMEM_HEAD + (size_t)stages * stage_bytes;
-    static size_t attr_set[2][NV] = {};
-    if (smem > attr_set[ph][vi]) {
-        if (!cuda_ok(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute"))
-            return false;
-        attr_set[ph][vi] = smem;
-        if (env_int("FCT_VERBOSE", 0))
-            std::fprintf(stderr, "fesom2-accelerate: warp kernel %c: %d stages of %d B, %d consumer + %d issuer warps\n",
-                         isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers);
-    }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev_id = 0;
-        cudaGetDevice(&dev_id);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-        sms = std::max(sms, 1);
-    }
+    bool first = false;
+    if (!ensure_smem_attr(reinterpret_cast<const void *>(v.fn), smem, &first)) return false;
+    if (first && env_int("FCT_VERBOSE", 0))
+        std::fprintf(stderr, "fesom2-accelerate: warp kernel %c: %d stages of %d B, %d consumer + %d issuer warps\n",
+                     isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers);
+    const int sms = device_sms();
     const long long total = (long long)T.ntiles * ntracers;
     if (total >= (1LL << 30)) {
         std::fprintf(stderr, "fesom2-accelerate: too many (tile, tracer) pairs for one launch\n");
@@ -506,32 +534,29 @@ bool launch_tile(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     const bool isA = stage == ST_PHASE_A;
     TileDev T = p->tiles[isA ? 0 : 1][which];
     if (T.ntiles <= 0) return true;
-    const int ai = isA ? 0 : 1;
     constexpr int NV = 6;
-    static size_t attr_set[2][NV] = {};
-    static size_t occ_smem[2][NV] = {};
-    static int resident[2][NV] = {};
     const int vi = std::min(std::max(env_int(isA ? "FCT_TILE_VARIANT_A" : "FCT_TILE_VARIANT_B", 0), 0), NV - 1);
     const TileVariant &v = isA ? g_variants_a[vi] : g_variants_b[vi];
     const size_t smem = tile_smem_bytes(isA, A.pitchL, T.TN, T.TE, T.max_rows);
-    if (smem > attr_set[ai][vi]) {
-        if (!cuda_ok(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute"))
-            return false;
-        attr_set[ai][vi] = smem;
+    if (!ensure_smem_attr(reinterpret_cast<const void *>(v.fn), smem)) return false;
+    // tables of the tile one "resident wave" ahead are prefetched into L2; occupancy per (device, kernel, smem)
+    int resident = 0;
+    {
+        static std::map<std::tuple<int, const void *, size_t>, int> occ;
+        const int sms = device_sms();
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        int &r = occ[std::make_tuple(current_device(), reinterpret_cast<const void *>(v.fn), smem)];
+        if (r == 0) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, TILE_THREADS, smem) != cudaSuccess) per_sm = 2;
+            r = std::max(per_sm, 1) * sms;
+            if (env_int("FCT_VERBOSE", 0))
+                std::fprintf(stderr, "fesom2-accelerate: phase %c tile kernel %s: %zu B smem, %d CTAs/SM\n",
+                             isA ? 'A' : 'B', v.name, smem, per_sm);
+        }
+        resident = r;
     }
-    if (smem != occ_smem[ai][vi]) {
-        // tables of the tile one "resident wave" ahead are prefetched into L2
-        int per_sm = 0, dev_id = 0, sms = 0;
-        cudaGetDevice(&dev_id);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, TILE_THREADS, smem) != cudaSuccess) per_sm = 2;
-        resident[ai][vi] = std::max(per_sm, 1) * std::max(sms, 1);
-        occ_smem[ai][vi] = smem;
-        if (env_int("FCT_VERBOSE", 0))
-            std::fprintf(stderr, "fesom2-accelerate: phase %c tile kernel %s: %zu B smem, %d CTAs/SM\n",
-                         isA ? 'A' : 'B', v.name, smem, per_sm);
-    }
-    T.ahead = env_int("FCT_TILE_AHEAD", resident[ai][vi]);
+    T.ahead = env_int("FCT_TILE_AHEAD", resident);
     dim3 grid(T.ntiles, ntracers, 1);
     v.fn<<<grid, TILE_THREADS, smem, s>>>(A, T);
     count_launch(1);
@@ -728,7 +753,11 @@ void make_stream_(void **stream, int *istat)
 {
     *istat = 0;
     cudaStream_t *s = new cudaStream_t;
-    if (!cuda_ok(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate")) {
+    // a blocking stream, as the reference creates it (src/fesom2-accelerate.cu:174): it serialises with
+    // the legacy default stream, so the synchronous calls of the ABI (transfer_var_, transfer_mesh_,
+    // transfer_var_back_: plain cudaMemcpy on the null stream) wait for the kernels and copies queued
+    // on it and vice versa -- the implicit ordering an unmodified caller relies on
+    if (!cuda_ok(cudaStreamCreate(s), "cudaStreamCreate")) {
         std::fprintf(stderr, "fesom2-accelerate: stream creation failed, returning the default stream\n");
         *s = (cudaStream_t)0;
         *istat = 1;

@@ -217,7 +217,12 @@ static void fused_step(Fields *f, Halo *h, cudaStream_t s, const Arrays &A, int 
     if (!cuda_ok(cudaEventRecord(halo_event(h, 0), s), "event") ||
         !cuda_ok(cudaStreamWaitEvent(c, halo_event(h, 0), 0), "wait"))
         return;
-    if (!halo_exchange(f, h, c)) return;
+    // knob HALO_SKIP (timing experiment only, wrong halo rows): the same launches without the exchange,
+    // so that the exposed part of the communication can be measured as a difference of step times
+    const bool skip = tune_int("FCT_HALO_SKIP", 0) != 0;
+    if (!cuda_ok(cudaEventRecord(halo_timing_event(h, 0), c), "event")) return;
+    if (!skip && !halo_exchange(f, h, c)) return;
+    if (!cuda_ok(cudaEventRecord(halo_timing_event(h, 1), c), "event")) return;
     if (!cuda_ok(cudaEventRecord(halo_event(h, 1), c), "event")) return;
     if (!phase(ST_PHASE_A, 2)) return;
     *alg_state = 6;

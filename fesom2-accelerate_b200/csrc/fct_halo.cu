@@ -32,6 +32,9 @@ struct Halo {
     size_t sendbuf_doubles = 0;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // timing events around the exchange of the overlapped step (fct_ale_halo_comm_ms_)
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    bool timed = false;
 };
 
 // NCCL is bound at first use, not at link time: a host process that already carries an NCCL (for
@@ -90,6 +93,11 @@ static const NcclApi &nccl()
 bool halo_valid(Halo *h) { return h && h->magic == HALO_MAGIC; }
 cudaStream_t halo_comm_stream(Halo *h) { return h->comm_stream; }
 cudaEvent_t halo_event(Halo *h, int which) { return h->ev[which]; }
+cudaEvent_t halo_timing_event(Halo *h, int which)
+{
+    h->timed = true;
+    return h->tev[which];
+}
 
 static bool nccl_ok(ncclResult_t r, const char *what)
 {
@@ -268,6 +276,32 @@ void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int 
         off += send_counts[k];
     }
     h->total_send = off;
+    // every id is checked before anything indexes with it: send nodes are owned BOUNDARY nodes of the
+    // plan (the overlapped step sends right after phase A of the boundary set: any other node's
+    // factors would leave stale), receive ranges lie inside the halo rows [N, N + H]
+    for (int i = 0; i < off; ++i) {
+        const int n = send_nodes[i];
+        if (n < 0 || n >= p->N) {
+            std::fprintf(stderr, "fesom2-accelerate: halo send node %d is not an owned node\n", n);
+            delete h;
+            return;
+        }
+        if (!p->boundary_flag.empty() && !p->boundary_flag[(size_t)n]) {
+            std::fprintf(stderr, "fesom2-accelerate: halo send node %d has no halo neighbour in the plan's mesh\n", n);
+            delete h;
+            return;
+        }
+    }
+    for (int k = 0; k < *npeers; ++k) {
+        const long long r0 = recv_first[k], rn = recv_counts[k];
+        if (peer_ranks[k] < 0 || peer_ranks[k] >= *nranks || peer_ranks[k] == *rank || send_counts[k] < 0 || rn < 0 ||
+            (rn > 0 && (r0 < p->N || r0 + rn > (long long)p->N + p->H))) {
+            std::fprintf(stderr, "fesom2-accelerate: halo peer %d: receive range [%lld, %lld) outside the halo rows [%d, %d) or bad rank / count\n",
+                         peer_ranks[k], r0, r0 + rn, p->N, p->N + p->H);
+            delete h;
+            return;
+        }
+    }
     bool ok = cuda_ok(cudaMalloc(&h->d_send_nodes, (size_t)(off > 0 ? off : 1) * sizeof(int)), "cudaMalloc(halo)");
     if (ok && off > 0)
         ok = cuda_ok(cudaMemcpy(h->d_send_nodes, send_nodes, (size_t)off * sizeof(int), cudaMemcpyHostToDevice), "H2D(halo)");
@@ -275,11 +309,6 @@ void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int 
         h->send_col.assign((size_t)off + 1, 0u);
         for (int i = 0; i < off && ok; ++i) {
             const int n = send_nodes[i];
-            if (n < 0 || n >= p->N) {
-                std::fprintf(stderr, "fesom2-accelerate: halo send node %d is not an owned node\n", n);
-                ok = false;
-                break;
-            }
             h->send_col[i + 1] = h->send_col[i] + (p->ncol[n + 1] - p->ncol[n]);
         }
         ok = ok && cuda_ok(cudaMalloc(&h->d_send_col, h->send_col.size() * sizeof(unsigned)), "cudaMalloc(halo)") &&
@@ -288,6 +317,7 @@ void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int 
     ok = ok && cuda_ok(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking), "stream");
     ok = ok && cuda_ok(cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming), "event");
     ok = ok && cuda_ok(cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming), "event");
+    ok = ok && cuda_ok(cudaEventCreate(&h->tev[0]), "event") && cuda_ok(cudaEventCreate(&h->tev[1]), "event");
     if (ok) {
         ncclUniqueId id;
         std::memcpy(&id, id128, 128);
@@ -315,9 +345,27 @@ void fct_ale_halo_destroy_(void **halo, int *istat)
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : h->tev)
+        if (e) cudaEventDestroy(e);
     h->magic = 0;
     delete h;
     *halo = nullptr;
+    *istat = 0;
+}
+
+// Device time of the last overlapped step's exchange on the halo's own stream (pack kernel + grouped
+// send / recv, including the wait for the slowest peer).  Synchronises on that exchange.
+void fct_ale_halo_comm_ms_(void **halo, real_type *ms, int *istat)
+{
+    Halo *h = (halo && *halo) ? static_cast<Halo *>(*halo) : nullptr;
+    *istat = 1;
+    *ms = 0.;
+    if (!halo_valid(h) || !h->timed) return;
+    float t = 0.f;
+    if (!cuda_ok(cudaEventSynchronize(h->tev[1]), "cudaEventSynchronize") ||
+        !cuda_ok(cudaEventElapsedTime(&t, h->tev[0], h->tev[1]), "cudaEventElapsedTime"))
+        return;
+    *ms = (double)t;
     *istat = 0;
 }
 

@@ -61,6 +61,7 @@ bool halo_exchange_field(Fields *f, Halo *h, cudaStream_t s, int field);
 // streams / events used to overlap the exchange with interior work
 cudaStream_t halo_comm_stream(Halo *h);
 cudaEvent_t halo_event(Halo *h, int which);
+cudaEvent_t halo_timing_event(Halo *h, int which);   // timing-enabled pair around the exchange
 bool halo_valid(Halo *h);
 
 }   // namespace fct

@@ -45,6 +45,12 @@ bool build_derived(int N, int H, int E, int G, int nl, const int *nlev_e, const 
             std::fprintf(stderr, "fct plan: edge %d has an element outside [1,%d]\n", g + 1, E);
             return false;
         }
+        if (a >= N && b >= N) {
+            // myDim_edge2D holds the edges that touch an owned node; an edge between two
+            // halo nodes would have no node to store its limited flux in the fused phase B
+            std::fprintf(stderr, "fct plan: edge %d joins two halo nodes (no owned end): not a FESOM myDim_edge2D edge\n", g + 1);
+            return false;
+        }
         const int d1 = nlev_e[el] - 1;
         const int d2 = (er >= 0) ? nlev_e[er] - 1 : 0;
         const int depth = std::max(std::max(d1, d2), 0);
@@ -237,15 +243,29 @@ static void schedule_node(std::vector<unsigned short> *v, size_t &len, int ln, i
 // Column offsets (in doubles) of the packed level storage: node n owns [ncol[n], ncol[n+1]), an even
 // number of slots that holds its nlev-1 active levels plus the bottom interface (fct_adf_v, area);
 // edge g owns [ecol[g], ecol[g+1]), its active levels rounded up to even.
-void packed_columns(const DerivedHost &d, const int *nlev_n, int NT, int G, std::vector<unsigned> &ncol,
+bool packed_columns(const DerivedHost &d, const int *nlev_n, int NT, int G, std::vector<unsigned> &ncol,
                     std::vector<unsigned> &ecol)
 {
+    // 32-bit element offsets: what the blobs, the copy lists and the kernels carry.  A mesh whose
+    // packed node or edge array does not fit them is refused (the caller falls back / reports istat 1)
+    const unsigned long long LIMIT = 0xffffffffull - 4096ull;
+    unsigned long long acc = 0;
     ncol.assign((size_t)NT + 1, 0u);
-    for (int n = 0; n < NT; ++n) ncol[n + 1] = ncol[n] + (unsigned)((std::max(nlev_n[n] - 1, 0) + 2) & ~1);
+    for (int n = 0; n < NT; ++n) {
+        acc += (unsigned long long)((std::max(nlev_n[n] - 1, 0) + 2) & ~1);
+        if (acc > LIMIT) return false;
+        ncol[n + 1] = (unsigned)acc;
+    }
     std::vector<int> depth((size_t)std::max(G, 1), 0);
     for (size_t k = 0; k < d.edg.size(); ++k) depth[d.edg[k].x] = FCT_META_DEPTH(d.edg[k].z);
     ecol.assign((size_t)G + 1, 0u);
-    for (int g = 0; g < G; ++g) ecol[g + 1] = ecol[g] + (unsigned)((depth[g] + 1) & ~1);
+    acc = 0;
+    for (int g = 0; g < G; ++g) {
+        acc += (unsigned long long)((depth[g] + 1) & ~1);
+        if (acc > LIMIT) return false;
+        ecol[g + 1] = (unsigned)acc;
+    }
+    return true;
 }
 
 bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P, const unsigned *ncol,
@@ -527,7 +547,10 @@ extern "C" void fct_ale_plan_inspect_(int *myDim_nod2D, int *eDim_nod2D, int *my
     const int P = (*nl + 7) & ~7;
     // *packed != 0: the packed level storage (columns hold their slots back to back)
     std::vector<unsigned> ncol, ecol;
-    if (*packed) packed_columns(d, nlevels_nod2D, N + H, *myDim_edge2D, ncol, ecol);
+    if (*packed && !packed_columns(d, nlevels_nod2D, N + H, *myDim_edge2D, ncol, ecol)) {
+        *istat = 2;   // packed offsets would not fit 32 bits
+        return;
+    }
     if (!build_warptiles(d, nlevels_nod2D, N, N + H, *myDim_edge2D, P, *packed ? ncol.data() : nullptr,
                          *packed ? ecol.data() : nullptr, list, *tile_nodes, *smem_cap, h)) {
         *istat = 2;   // mesh not eligible

@@ -60,7 +60,8 @@ struct WarpTilesHost {
 // layout (row = index * P).
 bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int G, int P, const unsigned *ncol,
                      const unsigned *ecol, const std::vector<int> *list, int TN, int smem_cap, WarpTilesHost &out);
-void packed_columns(const DerivedHost &d, const int *nlev_n, int NT, int G, std::vector<unsigned> &ncol,
+// false: an offset would not fit 32 bits
+bool packed_columns(const DerivedHost &d, const int *nlev_n, int NT, int G, std::vector<unsigned> &ncol,
                     std::vector<unsigned> &ecol);
 
 struct Plan {
@@ -82,6 +83,7 @@ struct Plan {
     const unsigned *d_ncol = nullptr, *d_ecol = nullptr;
     WarpTilesDev wtiles_pk[3] = {};
     bool wtiles_pk_ok = false;
+    std::vector<unsigned char> boundary_flag;   // host: [N] 1 = owned node with a halo neighbour (halo validation)
     std::vector<void *> owned;   // device allocations to free
 };
 

@@ -206,6 +206,14 @@ class HaloLink:
             raise abi.AbiError("fct_ale_comm_unique_id_ failed")
         return buf.raw
 
+    def comm_ms(self) -> float:
+        """Device time of the exchange inside the last overlapped step (synchronises on it)."""
+        ms, st = C.c_double(), C.c_int()
+        self.lib.fct_ale_halo_comm_ms_(C.byref(self.h), C.byref(ms), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("fct_ale_halo_comm_ms_ failed (no overlapped step yet?)")
+        return ms.value
+
     def free(self):
         st = C.c_int()
         self.lib.fct_ale_halo_destroy_(C.byref(self.h), C.byref(st))

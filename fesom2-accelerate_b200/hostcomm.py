@@ -76,3 +76,12 @@ def exchange_nod(part, arrays):
         b = buf.numpy()
         for i, a in enumerate(arrays):
             a[first:first + cnt] = b[i]
+
+
+def sum_mod64(x: int) -> int:
+    """Sum of one Python integer per rank, modulo 2^64 (digests)."""
+    if world()[1] == 1:
+        return int(x) & 0xFFFFFFFFFFFFFFFF
+    vals = [None] * world()[1]
+    _dist().all_gather_object(vals, int(x))
+    return sum(vals) & 0xFFFFFFFFFFFFFFFF

@@ -480,22 +480,39 @@ def fast_fields(mesh: Mesh, seed: int = 1, alloc=None, with_uv: bool = False) ->
     """Benchmark-sized synthetic fields in seconds rather than minutes: every array is filled by
     tiling one random block (different phase and affine map per array).  Same value ranges as
     make_fields; no poisoning and no zeroing below the sea floor (those cells are never used).
-    `alloc(shape)` lets the caller place the arrays in page-locked memory."""
+    `alloc(shape)` lets the caller place the arrays in page-locked memory.
+
+    The value of a cell is a function of its GLOBAL row id (mesh.node_gid / edge_gid / elem_gid when
+    the mesh is a partition, else the row index), its column, the array and the seed only: the
+    partitions of a mesh hold exactly the rows of the single-domain arrays, whatever the number of
+    partitions (what bench.py's digest of the outputs relies on)."""
     rng = np.random.default_rng(seed)
     alloc = alloc or (lambda shape: np.empty(shape, dtype=np.float64))
     B = 1 << 22
     base = rng.standard_normal(B + 4096)
     NT, L, nl, G = mesh.nnod, mesh.L, mesh.nl, mesh.myDim_edge2D
 
-    def fill(shape, scale, offset, phase, clip=None):
+    def fill(shape, scale, offset, phase, clip=None, kind="node"):
         a = alloc(shape)
-        flat = a.reshape(-1)
         blk = base[phase: phase + B] * scale + offset
         if clip is not None:
             np.clip(blk, clip[0], clip[1], out=blk)
-        for i in range(0, flat.size, B):
-            n = min(B, flat.size - i)
-            flat[i:i + n] = blk[:n]
+        gid = {"node": mesh.node_gid, "edge": mesh.edge_gid, "elem": mesh.elem_gid}[kind]
+        if gid is None:
+            flat = a.reshape(-1)
+            for i in range(0, flat.size, B):
+                n = min(B, flat.size - i)
+                flat[i:i + n] = blk[:n]
+            return a
+        # partition: row r of the local array is row gid[r] of the single-domain array
+        W = int(np.prod(shape[1:]))
+        a2 = a.reshape(shape[0], W)
+        cols = np.arange(W, dtype=np.int64)[None, :]
+        step = max(1, (1 << 22) // max(W, 1))
+        g64 = np.asarray(gid, dtype=np.int64)
+        for r in range(0, shape[0], step):
+            idx = (g64[r:r + step, None] * W + cols) & (B - 1)
+            a2[r:r + step] = blk[idx]
         return a
 
     ttf = fill((NT, L), 0.1, 10.0, 0)
@@ -508,10 +525,42 @@ def fast_fields(mesh: Mesh, seed: int = 1, alloc=None, with_uv: bool = False) ->
     hnode_new = fill((NT, L), 10.0, 27.0, 211, clip=(5.0, 50.0))
     hnode_new *= 1.0 + 1e-3 * base[307]
     f = Fields(
-        ttf=ttf, fct_LO=lo, fct_adf_v=fill((NT, nl), 1.0, 0.0, 401), fct_adf_h=fill((G, L), 1.0, 0.0, 503),
+        ttf=ttf, fct_LO=lo, fct_adf_v=fill((NT, nl), 1.0, 0.0, 401), fct_adf_h=fill((G, L), 1.0, 0.0, 503, kind="edge"),
         area=area, area_inv=area_inv, hnode=hnode, hnode_new=hnode_new,
         del_ttf_advvert=fill((NT, L), 1.0, 0.0, 601), del_ttf_advhoriz=fill((NT, L), 1.0, 0.0, 701),
         fct_ttf_max=fill((NT, L), 0.0, SENTINEL, 0), fct_ttf_min=fill((NT, L), 0.0, SENTINEL, 0),
         fct_plus=fill((NT, L), 0.0, SENTINEL, 0), fct_minus=fill((NT, L), 0.0, SENTINEL, 0),
-        UV_rhs=fill((mesh.myDim_elem2D, L, 2), 0.0, SENTINEL, 0) if with_uv else None)
+        UV_rhs=fill((mesh.myDim_elem2D, L, 2), 0.0, SENTINEL, 0, kind="elem") if with_uv else None)
     return f
+
+
+# ----------------------------------------------------------------------------------------------
+# Order-independent digest of a node array over the OWNED, ACTIVE cells of a (partition of a) mesh:
+# the sum modulo 2^64 of a 64-bit mix of (global node id, level, value bits).  The digests of the
+# partitions of a mesh add up (mod 2^64) to the digest of the single-domain array exactly when every
+# owned cell holds the same bits, whatever the number of partitions (bench.py: `digest`).
+# ----------------------------------------------------------------------------------------------
+_M1 = np.uint64(0x9E3779B97F4A7C15)
+_M2 = np.uint64(0xBF58476D1CE4E5B9)
+_M3 = np.uint64(0x94D049BB133111EB)
+
+
+def digest_node_array(mesh: Mesh, a: np.ndarray, salt: int = 0) -> int:
+    n = mesh.myDim_nod2D
+    W = a.shape[1]
+    gid = np.arange(n, dtype=np.int64) if mesh.node_gid is None else np.asarray(mesh.node_gid[:n], dtype=np.int64)
+    cols = np.arange(W, dtype=np.uint64)[None, :]
+    depth = (mesh.nlevels_nod2D[:n].astype(np.int64) - 1)[:, None]
+    total = 0
+    step = max(1, (1 << 22) // max(W, 1))
+    with np.errstate(over="ignore"):
+        for r in range(0, n, step):
+            v = (a[r:min(r + step, n)] + 0.0).view(np.uint64)          # + 0.0: -0 and +0 are the same value
+            key = (gid[r:r + step, None].astype(np.uint64) * np.uint64(W) + cols + np.uint64(salt)) * _M1
+            h = (v ^ key) * _M2
+            h ^= h >> np.uint64(29)
+            h *= _M3
+            h ^= h >> np.uint64(32)
+            act = np.arange(W)[None, :] < depth[r:r + step]
+            total = (total + int(h[act].sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+    return total

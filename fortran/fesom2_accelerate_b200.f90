@@ -175,6 +175,13 @@ module fesom2_accelerate_b200
       type(c_ptr) :: fields, halo, stream
       integer(c_int) :: istat
     end subroutine
+    ! device time (ms) of the exchange inside the last overlapped step that used this halo
+    subroutine fct_ale_halo_comm_ms(halo, ms, istat) bind(C, name="fct_ale_halo_comm_ms_")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr) :: halo
+      real(c_double) :: ms
+      integer(c_int) :: istat
+    end subroutine
     ! exchange_nod of one per-tracer node array of width nl-1 (FCT_LO, FCT_TTF, ...)
     subroutine fct_ale_halo_exchange_field(fields, halo, stream, field, istat) bind(C, name="fct_ale_halo_exchange_field_")
       import :: c_int, c_ptr

@@ -292,11 +292,18 @@ void fct_ale_comm_unique_id_(char *id128, int *istat);
 /* Per-rank halo descriptor.  send_nodes: concatenated 0-based local owned node ids, send_counts[p]
  * of them for peer_ranks[p], in the order of the receiver's halo numbering; the rows received from
  * peer p land in local nodes [recv_first[p], recv_first[p]+recv_counts[p]) (halo nodes are grouped
- * by owner). */
+ * by owner).  Every id is validated (istat = 1): send nodes must be owned nodes with a halo
+ * neighbour in the plan's mesh, receive ranges must lie inside the halo rows. */
 void fct_ale_halo_create_(void **halo, void **plan, char *id128, int *rank, int *nranks, int *npeers,
                           int *peer_ranks, int *send_counts, int *send_nodes, int *recv_first,
                           int *recv_counts, int *istat);
 void fct_ale_halo_destroy_(void **halo, int *istat);
+/* Device time (ms, CUDA events on the halo's own stream) of the exchange inside the last
+ * fct_ale_step_ / fct_ale_step_general_ that used this halo: pack kernel + grouped send / recv,
+ * including the wait for the slowest peer.  Synchronises on that exchange.  Tuning knob
+ * "HALO_SKIP" 1 runs the same launches WITHOUT the exchange (timing experiment, stale halo rows):
+ * step time minus that = the part of the communication the overlap does not hide. */
+void fct_ale_halo_comm_ms_(void **halo, real_type *ms, int *istat);
 /* the exchange alone (tests, timing) */
 void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *istat);
 /* exchange_nod of ONE per-tracer node array of width nl-1 (*field: FCT_LO between two passes of

@@ -576,3 +576,33 @@ def test_full_size_properties(mesh_mod, harness):
     assert abs(w[act].sum()) <= 1e-9 * np.abs(w[act]).sum()
     df.free()
     plan.free()
+
+
+def test_benchmark_scale_mesh_against_the_full_oracle(mesh_mod, harness, abi, oracle_mod):
+    """A 1.8 M-node, 70-level mesh (a quarter of the NG5 workload: 50 000 tiles, the two-stage ring with
+    the copy lists ahead that bench.py's default picks for nl >= 60, 10^8-element edge offsets) through
+    the packed warp-item path, every output compared bit for bit with the full CPU oracle -- the
+    configuration that is benchmarked is also a configuration that is checked."""
+    m = mesh_mod.make_mesh(1560, 1204, 70, seed=0)
+    assert m.myDim_nod2D > 1_800_000
+    f = mesh_mod.fast_fields(m, seed=7, with_uv=True)
+    # an out-of-depth read must show up in the results: poison the inactive levels of the inputs
+    dead = np.arange(m.L)[None, :] >= (m.nlevels_nod2D[:, None] - 1)
+    for k, v in (("ttf", 1e30), ("fct_LO", -1e30), ("hnode", 1e30), ("hnode_new", 1e30)):
+        getattr(f, k)[dead] = v
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    f.UV_rhs = None
+    want.UV_rhs = None
+    plan = harness.DevicePlan(m)
+    assert plan.packed_ok
+    df = harness.DeviceFields(plan, 1, packed=True)
+    df.upload(f)
+    for rep in range(2):                     # the second pass re-arms the device-wide tile counters
+        if rep:
+            for k in ("del_ttf_advvert", "del_ttf_advhoriz"):
+                df.upload_field(k, getattr(f, k))
+        assert df.step(f, mode=1) == 10
+        check(df.download(f, mode=1), want)
+    df.free()
+    plan.free()
