@@ -302,6 +302,33 @@ def workload_config(name, gm):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+REF_GPU_SO = os.path.join(ROOT, "baseline", "_ref", "libref_gpu_kernels.so")
+REF_GPU_STAGES = ["a1", "a2", "a3", "b1v", "b1h_grid_nodes_as_shipped", "b1h", "b2", "b3v", "b3h", "cv", "ch", "sequence"]
+
+
+def gpu_reference(m, abi, reps=3):
+    """The reference's OWN kernels (/root/reference/kernels/*.cu compiled unmodified for sm_100 by
+    baseline/build_ref_gpu.sh) on the workload mesh, device-resident, CUDA events, launched with the
+    reference driver's geometry (src/fesom2-accelerate.cu:294-335).  Timing only: the reference launches
+    b1_horizontal over nodes instead of edges (:327), its results are not a parity oracle."""
+    if not os.path.exists(REF_GPU_SO):
+        return {"unavailable": "baseline/_ref/libref_gpu_kernels.so not built (needs /root/reference at build time)"}
+    import ctypes as C
+    lib = C.CDLL(REF_GPU_SO)
+    ms = (C.c_double * 12)()
+    st = C.c_int()
+    ci, ip = abi.ci, abi.iptr
+    lib.ref_gpu_bench_(ci(m.myDim_nod2D), ci(m.eDim_nod2D), ci(m.myDim_elem2D), ci(m.myDim_edge2D), ci(m.nl),
+                       ip(m.nlevels_nod2D), ip(m.nlevels_elem), ip(m.elem2D_nodes.reshape(-1)), ip(m.nod_in_elem2D_num),
+                       ip(m.nod_in_elem2D.reshape(-1)), ci(m.nod_in_elem2D_dim), ip(m.edges.reshape(-1)),
+                       ip(m.edge_tri.reshape(-1)), ci(reps), ms, C.byref(st))
+    if st.value != 0:
+        return {"unavailable": "ref_gpu_bench_ failed (see stderr)"}
+    return {"stages_ms": dict(zip(REF_GPU_STAGES[:11], [float(x) for x in ms][:11])), "step_ms": float(ms[11]),
+            "what": "reference kernels rebuilt for sm_100 (baseline/_ref), one 32-thread block per node / element / edge, fp64 atomics in "
+                    "b1h / c_h; sequence = a1..c with b1h over edges; device-resident, CUDA events; timing only"}
+
+
 PARITY_KEYS = ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "del_ttf_advvert", "del_ttf_advhoriz")
 
 
@@ -518,17 +545,63 @@ def run_product(args):
     log(f"value done: {ms_step:.3f} ms/step ({time.time() - t_setup:.1f}s)")
 
     # ---------------- e2e: host-resident caller, device-resident step ----------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    # (1) one model TIME STEP of E2E_TRACERS tracers (T, S + 10 passive: BASELINE.json config 5's batch, the way
+    #     FESOM2 calls fct_ale): hnode / hnode_new -- inputs of the time step, constant across its tracers --
+    #     uploaded once, the six per-tracer arrays uploaded and the two tendencies downloaded for every tracer,
+    #     all inside the timed region, dense page-locked host arrays.  This is `e2e.value`, per tracer step.
+    # (2) the same for a caller that keeps its columns in the packed level storage on the host (70 % of the bytes).
+    # (3) the round-1 pattern: every tracer step uploads all eight arrays (`single_tracer`).
+    T_E2E = max(1, args.e2e_tracers)
+    per_tracer = [k for k in df.STEP_INPUTS if k not in ("hnode", "hnode_new")]
     assert df.host_step(f, f, mode=1, halo=halo) == 10       # warm-up
     hostcomm.barrier()
     ta = time.perf_counter()
-    # every step uploads its inputs and downloads its tendencies; the download of step k (second
-    # stream) overlaps the upload of step k+1; ends with await_stream_: the tendencies are on the host
+    assert df.host_steps_batch(f, f, T_E2E, mode=1, halo=halo) == 10     # ends with await_stream_: tendencies on the host
+    tb = time.perf_counter()
+    e2e_s = hostcomm.max_over_ranks((tb - ta) / T_E2E)
+    hb = sum(df.link_bytes(k, getattr(f, k), True) for k in per_tracer) + sum(df.link_bytes(k, getattr(f, k), True) for k in ("hnode", "hnode_new")) / T_E2E
+    db = sum(df.link_bytes(k, getattr(f, k), False) for k in df.STEP_RESULTS)
+    h2d, d2h = hostcomm.sum_over_ranks(hb), hostcomm.sum_over_ranks(db)
+    log(f"e2e (time step of {T_E2E} tracers, dense host arrays): {e2e_s * 1e3:.1f} ms per tracer step ({time.time() - t_setup:.1f}s)")
+    # (3) single tracer steps, everything uploaded every step
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    hostcomm.barrier()
+    ta = time.perf_counter()
     assert df.host_steps(f, f, e2e_steps, mode=1, halo=halo) == 10
     tb = time.perf_counter()
-    e2e_s = hostcomm.max_over_ranks((tb - ta) / e2e_steps)
-    hb, db = df.host_step_bytes(f)
-    h2d, d2h = hostcomm.sum_over_ranks(hb), hostcomm.sum_over_ranks(db)
+    single_s = hostcomm.max_over_ranks((tb - ta) / e2e_steps)
+    shb, sdb = df.host_step_bytes(f)
+    single = {"value": Sn_total / single_s, "unit": UNIT, "ms_per_step": single_s * 1e3, "steps": e2e_steps,
+              "h2d_bytes_per_step": int(hostcomm.sum_over_ranks(shb)), "d2h_bytes_per_step": int(hostcomm.sum_over_ranks(sdb)),
+              "api": "per tracer step: fct_ale_field_upload_ x8 / fct_ale_step_ / fct_ale_field_download_ x2 (round-1 pattern)"}
+    # (2) packed host arrays
+    packed_host = None
+    if df.packed:
+        ph, nbytes_up, nbytes_dn = {}, 0, 0
+        for k in df.STEP_INPUTS:
+            # the packed host image of the array, produced by the device (upload dense, download packed):
+            # set-up only, outside every timed region
+            kind = "edge" if k == "fct_adf_h" else "node"
+            ph[k] = abi.pinned_empty(int(plan.packed_columns(kind)[-1]))
+            df.upload_field(k, getattr(f, k))
+            df.download_packed(k, ph[k])
+            df.stream.sync()
+            nbytes_up += ph[k].nbytes / (T_E2E if k in ("hnode", "hnode_new") else 1)
+        for k in df.STEP_RESULTS:
+            ph["out_" + k] = ph[k]
+            nbytes_dn += ph[k].nbytes
+        assert df.host_steps_batch(f, f, 1, mode=1, halo=halo, packed_host=ph) == 10
+        hostcomm.barrier()
+        ta = time.perf_counter()
+        assert df.host_steps_batch(f, f, T_E2E, mode=1, halo=halo, packed_host=ph) == 10
+        tb = time.perf_counter()
+        pk_s = hostcomm.max_over_ranks((tb - ta) / T_E2E)
+        packed_host = {"value": Sn_total / pk_s, "unit": UNIT, "ms_per_step": pk_s * 1e3, "tracers": T_E2E,
+                       "h2d_bytes_per_step": int(hostcomm.sum_over_ranks(nbytes_up)), "d2h_bytes_per_step": int(hostcomm.sum_over_ranks(nbytes_dn)),
+                       "api": "the same time step for a caller whose host arrays are already in the packed level storage: "
+                              "fct_ale_field_upload_packed_ / fct_ale_field_download_packed_ (one contiguous copy per array, no repack)"}
+        del ph
+        log(f"e2e packed host arrays: {pk_s * 1e3:.1f} ms per tracer step ({time.time() - t_setup:.1f}s)")
     if halo is not None:
         halo.free()
     df.free()
@@ -556,6 +629,15 @@ def run_product(args):
         ch.free()
         log(f"reference call sequence done: {rs * 1e3:.1f} ms/step ({time.time() - t_setup:.1f}s)")
 
+    # ---------------- the reference's own GPU kernels on the same mesh (N = 1) ----------------
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        gpu_ref = gpu_reference(m, abi)
+        if "step_ms" in gpu_ref:
+            gpu_ref["value"] = Sn_total / (gpu_ref["step_ms"] * 1e-3)
+            gpu_ref["speedup_of_this_repo"] = gpu_ref["step_ms"] / ms_step
+            log(f"reference GPU kernels: {gpu_ref['step_ms']:.2f} ms/step, this repo {ms_step:.2f} ms ({time.time() - t_setup:.1f}s)")
+
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -577,11 +659,14 @@ def run_product(args):
                 "hbm": {"alg_GBs_per_gpu": bytes_alg_total / world / ms_step / 1e6, "frac_of_peak": bytes_alg_total / world / ms_step / 1e6 / peak},
                 "clocks": clocks,
                 "e2e": {"value": Sn_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                        "api": "per step: fct_ale_field_upload_ x8 / fct_ale_step_ / fct_ale_field_download_ x2 on page-locked host arrays (download of step k on a second stream, overlapping the upload of step k+1), await_stream_ at the end",
+                        "ms_per_step": e2e_s * 1e3, "steps": T_E2E, "tracers_per_time_step": T_E2E,
+                        "api": "one model time step of 12 tracers on dense page-locked host arrays: fct_ale_field_upload_ of hnode, hnode_new once per time step, "
+                               "then per tracer fct_ale_field_upload_ x6 (ttf, fct_LO, fct_adf_v, fct_adf_h, del_ttf_adv*) / fct_ale_step_ / fct_ale_field_download_ x2 "
+                               "(download of tracer k on a second stream, overlapping the upload of tracer k+1), await_stream_ at the end; per tracer step",
+                        "single_tracer": single, "packed_host": packed_host,
                         "reference_sequence": refseq},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "parity": parity, "digest": digest, "preroll_s": preroll_s, "preroll_steps": n_pre, "halo": halo_info,
+                "gpu_reference": gpu_ref, "parity": parity, "digest": digest, "preroll_s": preroll_s, "preroll_steps": n_pre, "halo": halo_info,
                 "small_mesh_step_ms": floor_ms, "setup_s": time.time() - t_setup}
         _RESULT.append(json.dumps(line))
     if world > 1:
@@ -619,8 +704,10 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FCT_BENCH_WORKLOAD", "ng5"))
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-tracers", type=int, default=12, help="tracers of the time step the e2e leg times (T, S + 10 passive)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the timing of the reference's own GPU kernels")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs only)")
     ap.add_argument("--preroll", type=float, default=1.5, help="seconds of untimed steps before the timed region")
     ap.add_argument("--reference-budget", type=float, default=150.0, help="--impl reference: seconds of CPU steps after which no further step is started")

@@ -31,6 +31,7 @@ SYMBOLS = [
     "stress2rhs_plan_create_", "stress2rhs_plan_destroy_", "stress2rhs_acc_", "stress2rhs_", "fct_ale_stage_",
     "fct_ale_comm_unique_id_", "fct_ale_halo_create_", "fct_ale_halo_destroy_",
     "fct_ale_halo_exchange_", "fct_ale_halo_comm_ms_",
+    "fct_ale_plan_packed_size_", "fct_ale_plan_packed_columns_", "fct_ale_field_upload_packed_", "fct_ale_field_download_packed_",
 ]
 
 # enum fct_field_id

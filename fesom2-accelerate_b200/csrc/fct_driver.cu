@@ -394,11 +394,17 @@ struct WarpVariant {
     warp_kern_t fn;
     bool phase_a;
     int stages, consumers, issuers;
+    int regs = 0;   // > 0: roles re-allocate registers (setmaxnreg): 4 producer warps + consumers at `regs` each
 };
 // total warps (1 fetcher + issuers + [converter] + consumers) a multiple of 4: see fct_warp_kernels.cuh
 #define WT_VA(S, C, I) {k_phase_warp<true, S, C, I>, true, S, C, I}
 #define WT_VB(S, C, I) {k_phase_warp<false, S, C, I>, false, S, C, I}
+// register re-allocation between the roles: one producer warpgroup, whole consumer warpgroups
+#define WT_RA(S, C, I, R) {k_phase_warp<true, S, C, I, true, false, R>, true, S, C, I, R}
+#define WT_RB(S, C, I, R) {k_phase_warp<false, S, C, I, true, false, R>, false, S, C, I, R}
 static const WarpVariant g_wvariants[] = {
+    WT_RA(2, 24, 1, 80), WT_RA(3, 24, 1, 80), WT_RA(2, 20, 1, 88), WT_RA(3, 20, 1, 88),
+    WT_RB(2, 24, 1, 80), WT_RB(3, 24, 1, 80), WT_RB(2, 20, 1, 88), WT_RB(3, 20, 1, 88),
     WT_VA(3, 17, 4), WT_VA(3, 13, 4), WT_VA(3, 15, 6), WT_VA(3, 9, 4), WT_VA(3, 19, 2),
     WT_VA(2, 17, 4), WT_VA(2, 13, 4), WT_VA(2, 15, 6), WT_VA(2, 19, 2), WT_VA(4, 17, 4), WT_VA(4, 15, 6),
     WT_VB(3, 19, 4), WT_VB(3, 15, 4), WT_VB(3, 11, 4), WT_VB(3, 17, 6), WT_VB(3, 21, 2),
@@ -453,8 +459,20 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // 24 warps in all at 80 registers; the packed layout needs a sixth of the bulk copies: two issuers
     // (with the lists ahead the issuers also pull the rows into L2: four again, measured
     //  profiles/r1_v14_ab_ring_depth.log)
-    npw = npw <= 0 ? ((packed && stages != 2) ? 2 : 4) : npw;
-    nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
+    // knob WT_REGS: 0 = every warp at 80 registers (24 warps in all); 80 / 88 = the roles re-allocate
+    // registers (setmaxnreg): 4 producer warps at 24 + 24 consumers at 80 (28 warps launched at 72) or
+    // 20 consumers at 88 (24 warps launched at 80)
+    const bool plain = !iter && (!isA || A.vlimit == 1 || A.vlimit == 0);
+    int regs = plain ? env_int("FCT_WT_REGS", 0) : 0;
+    if (regs != 0 && regs != 80 && regs != 88) regs = 80;
+    if (regs > 0) {
+        npw = 1;   // one issuer warp: ~40 bulk copies per packed tile are two rounds of its 32 lanes
+        nwc = nwc <= 0 ? (regs == 80 ? 24 : 20) : nwc;
+        if (T.opt >= 0 && env_int("FCT_WT_OPT", -1) < 0) T.opt |= 1;   // few producers: suspended in hardware, not polling
+    } else {
+        npw = npw <= 0 ? ((packed && stages != 2) ? 2 : 4) : npw;
+        nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
+    }
     constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
     constexpr int NVI = sizeof(g_wvariants_it) / sizeof(g_wvariants_it[0]);
@@ -462,7 +480,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     const WarpVariant *table = vl ? g_wvariants_vl : (iter ? g_wvariants_it : g_wvariants);
     int vi = -1, best = 1 << 30;
     for (int i = 0; i < (vl ? NVL : (iter ? NVI : NV1)); ++i) {
-        if (table[i].stages != stages || table[i].phase_a != isA) continue;
+        if (table[i].stages != stages || table[i].phase_a != isA || table[i].regs != regs) continue;
         const int dist = 4 * std::abs(table[i].consumers - nwc) + std::abs(table[i].issuers - npw);
         if (dist < best) {
             best = dist;
@@ -506,7 +524,8 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         ctr = ring + 2 * (ctr_next.fetch_add(1) % CTR_SLOTS);
     }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
-    v.fn<<<grid, (v.issuers + 1 + (isA ? WT_CONVERTERS : 0) + v.consumers) * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
+    const int warps = v.regs > 0 ? WT_PRODUCER_WARPS + v.consumers : v.issuers + 1 + (isA ? WT_CONVERTERS : 0) + v.consumers;
+    v.fn<<<grid, warps * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");
 }

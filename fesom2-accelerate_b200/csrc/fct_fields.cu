@@ -442,6 +442,60 @@ static void field_copy(void **fields, int *field, int *tracer, real_type *host, 
     *istat = ok ? 0 : 1;
 }
 
+// ---- host arrays already in the packed level storage (a caller that keeps its columns packed) ----
+// One contiguous copy straight into / out of the device array: no staging buffer, no repack kernel, and
+// only the slots that exist cross the link (about 70 % of the dense array).
+static void field_copy_packed(void **fields, int *field, int *tracer, real_type *host, void **stream, int *istat, bool up)
+{
+    *istat = 1;
+    Fields *f = F_(fields);
+    if (f && (*field == FCT_ADF_V2 || *field == FCT_ADF_H2) && !ensure_iter_buffers(f)) return;
+    if (!f || !f->packed || *field < 0 || *field >= FCT_FIELD_COUNT || *field == FCT_UV_RHS || !f->buf[*field] || !host) {
+        if (f && !f->packed) std::fprintf(stderr, "fesom2-accelerate: packed host copies need fields in the packed level storage\n");
+        return;
+    }
+    const FieldMeta m = meta_of(*field);
+    const int t = m.per_tracer ? *tracer : 0;
+    if (t < 0 || t >= f->T) return;
+    const size_t n = m.kind == ROW_EDGE ? f->ts_edge : f->ts_node;
+    double *d = f->buf[*field] + (size_t)t * n;
+    cudaStream_t st = S_(stream);
+    const cudaError_t e = up ? cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, st)
+                             : cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    *istat = cuda_ok(e, up ? "packed field upload" : "packed field download") ? 0 : 1;
+}
+
+void fct_ale_field_upload_packed_(void **fields, int *field, int *tracer, real_type *host_packed, void **stream, int *istat)
+{
+    field_copy_packed(fields, field, tracer, host_packed, stream, istat, true);
+}
+
+void fct_ale_field_download_packed_(void **fields, int *field, int *tracer, real_type *host_packed, void **stream, int *istat)
+{
+    field_copy_packed(fields, field, tracer, host_packed, stream, istat, false);
+}
+
+void fct_ale_plan_packed_size_(void **plan, long long *node_doubles, long long *edge_doubles, int *istat)
+{
+    Plan *p = P_(plan);
+    *istat = 1;
+    *node_doubles = *edge_doubles = 0;
+    if (!p || !p->wtiles_pk_ok || p->ncol.empty() || p->ecol.empty()) return;
+    *node_doubles = (long long)p->ncol.back();
+    *edge_doubles = (long long)p->ecol.back();
+    *istat = 0;
+}
+
+void fct_ale_plan_packed_columns_(void **plan, int *kind, unsigned *columns, int *istat)
+{
+    Plan *p = P_(plan);
+    *istat = 1;
+    if (!p || !p->wtiles_pk_ok || !columns) return;
+    const std::vector<unsigned> &col = *kind == 1 ? p->ecol : p->ncol;
+    std::memcpy(columns, col.data(), col.size() * sizeof(unsigned));
+    *istat = 0;
+}
+
 void fct_ale_field_link_bytes_(void **fields, int *field, real_type *host, int *upload, long long *bytes)
 {
     *bytes = 0;

@@ -759,12 +759,40 @@ __device__ __forceinline__ void wt_item_b_iter(const Arrays &A, const WtView &V,
 // else: b3 vertical + b3 horizontal + c vertical + c horizontal.
 // dynamic smem: WT_SMEM_HEAD + NSTAGE * stage_bytes
 // ------------------------------------------------------------------------------------------------
-template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false>
-__global__ void __launch_bounds__((NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0) + NWC) * 32, 1)
+// RC > 0: register re-allocation between the warp roles (setmaxnreg).  The CTA is launched at <= 64
+// registers per thread; warps 0..3 form ONE producer warpgroup (fetcher, NPW issuers, in phase A the
+// converters; a warp without a role leaves at once) that shrinks to WT_PRODUCER_REGS, and the NWC
+// consumer warps (a multiple of 4: whole warpgroups) grow to RC each: 24 consumers at 80 registers
+// or 20 at 96 instead of 17..21 at 80 -- the producers no longer pin registers they never use.
+// setmaxnreg moves registers INSIDE the CTA's launch allocation (threads x registers of the compiled
+// kernel): the launch must already own what the roles hold afterwards.  28 warps x 72 registers = 64 512 =
+// 4 producer warps x 24 + 24 consumer warps x 80.
+constexpr int WT_PRODUCER_WARPS = 4;
+constexpr int WT_PRODUCER_REGS = 24;
+template <int N>
+__device__ __forceinline__ void reg_dealloc()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false, int RC = 0>
+__global__ void __launch_bounds__((RC > 0 ? WT_PRODUCER_WARPS : NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0)) * 32 + NWC * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
     extern __shared__ __align__(128) unsigned char wt_sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // first consumer warp
+    constexpr int NPROD = RC > 0 ? WT_PRODUCER_WARPS : NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0);
+    static_assert(RC == 0 || (NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0) <= WT_PRODUCER_WARPS && NWC % 4 == 0 &&
+                              WT_PRODUCER_WARPS * 32 * WT_PRODUCER_REGS + NWC * 32 * RC <=
+                                  (WT_PRODUCER_WARPS + NWC) * 32 * ((65536 / ((WT_PRODUCER_WARPS + NWC) * 32)) & ~7) &&
+                              RC % 8 == 0),
+                  "register budget of the re-allocated roles");
     const uint32_t bar = smem_u32(wt_sm);
     // barriers: [0,NSTAGE) stage empty, [NSTAGE,2N) blob landed, [2N,3N) rows landed, [3N,4N) a1 done,
     // [4N,5N) copy list landed in its slot, [5N,6N) copy list consumed
@@ -793,6 +821,10 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
         fence_mbar_init();
     }
     __syncthreads();
+    if (RC > 0) {
+        if (warp < WT_PRODUCER_WARPS) reg_dealloc<WT_PRODUCER_REGS>();
+        else reg_alloc<(RC > 0 ? RC : 80)>();
+    }
 
     if (warp == 0) {
         // ---- blob fetcher: refills a stage as soon as every consumer warp has left it.  Tiles are
@@ -928,7 +960,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             __syncwarp();
             if (lane == 0) mbar_arrive(b_ready(s));
         }
-    } else {
+    } else if (warp >= NPROD) {
         // ---- consumers ----
         auto draw = [&](int s) {   // lane 0 only; broadcast with __shfl_sync when needed
             int wi = 0;

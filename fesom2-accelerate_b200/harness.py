@@ -169,6 +169,45 @@ class DevicePlan:
         self.kernels = "warp" if wt.value else ("tile" if tt.value else "untiled")
         self.packed_ok = bool(pk.value)
 
+    def packed_columns(self, kind: str = "node") -> np.ndarray:
+        """Column offsets of the packed level storage: row r owns [col[r], col[r+1]) (uint32, in doubles)."""
+        m = self.m
+        rows = m.myDim_edge2D if kind == "edge" else m.nnod
+        col = np.zeros(rows + 1, np.uint32)
+        st = C.c_int()
+        self.lib.fct_ale_plan_packed_columns_(C.byref(self.h), ci(1 if kind == "edge" else 0),
+                                              col.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError("this plan has no packed level storage")
+        return col
+
+    def pack_host(self, dense: np.ndarray, kind: str = "node", out: Optional[np.ndarray] = None, alloc=None) -> np.ndarray:
+        """Dense host array [rows, W] -> packed host array (what a caller that keeps packed columns holds)."""
+        col = self.packed_columns(kind).astype(np.int64)
+        if out is None:
+            out = (alloc or np.empty)(int(col[-1]))
+        out[...] = 0.0
+        W = dense.shape[1]
+        cnt = np.minimum(np.diff(col), W)
+        step = max(1, (1 << 22) // max(W, 1))
+        cols = np.arange(W, dtype=np.int64)[None, :]
+        for r in range(0, dense.shape[0], step):
+            mask = cols < cnt[r:r + step, None]
+            dst = (col[r:r + step, None] + cols)[mask]
+            out[dst] = dense[r:r + step][mask]
+        return out
+
+    def unpack_host(self, packed: np.ndarray, dense: np.ndarray, kind: str = "node") -> np.ndarray:
+        col = self.packed_columns(kind).astype(np.int64)
+        W = dense.shape[1]
+        cnt = np.minimum(np.diff(col), W)
+        step = max(1, (1 << 22) // max(W, 1))
+        cols = np.arange(W, dtype=np.int64)[None, :]
+        for r in range(0, dense.shape[0], step):
+            mask = cols < cnt[r:r + step, None]
+            dense[r:r + step][mask] = packed[(col[r:r + step, None] + cols)[mask]]
+        return dense
+
     def free(self):
         st = C.c_int()
         self.lib.fct_ale_plan_destroy_(C.byref(self.h), C.byref(st))
@@ -372,6 +411,69 @@ class DeviceFields:
                                                  dptr(getattr(out, name).reshape(-1)), self._dn.ref, C.byref(stt))
                 if stt.value != 0:
                     raise abi.AbiError(f"download of {name} failed")
+            self._ev_dn.record(self._dn)
+        self._dn.sync()
+        self.stream.sync()
+        return st
+
+    # ---- host arrays already in the packed level storage ----
+    def upload_packed(self, name: str, host_packed: np.ndarray, tracer: int = 0, stream=None):
+        st = C.c_int()
+        self.lib.fct_ale_field_upload_packed_(C.byref(self.h), ci(abi.FIELD_IDS[name]), ci(tracer), dptr(host_packed),
+                                              (stream or self.stream).ref, C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError(f"packed upload of {name} failed")
+
+    def download_packed(self, name: str, host_packed: np.ndarray, tracer: int = 0, stream=None):
+        st = C.c_int()
+        self.lib.fct_ale_field_download_packed_(C.byref(self.h), ci(abi.FIELD_IDS[name]), ci(tracer), dptr(host_packed),
+                                                (stream or self.stream).ref, C.byref(st))
+        if st.value != 0:
+            raise abi.AbiError(f"packed download of {name} failed")
+
+    def host_steps_batch(self, f: Fields, out: Fields, tracers: int, mode: int = 1, halo: Optional[HaloLink] = None,
+                         packed_host: Optional[dict] = None) -> int:
+        """One model TIME STEP for a host-resident caller: `tracers` tracer steps back to back (T, S and
+        the passive tracers of docs/refactoring.md's caller), the mesh-static inputs of the step (hnode,
+        hnode_new: they move with the ALE surface once per time step, not per tracer) uploaded ONCE, the
+        per-tracer inputs (ttf, fct_LO, fct_adf_v, fct_adf_h, del_ttf_adv*) uploaded and the tendencies
+        downloaded for EVERY tracer; downloads on their own stream overlap the next tracer's uploads.
+        packed_host: name -> host array already in the packed level storage (then no repack, 70 % of
+        the bytes); else the dense arrays of `f` / `out`."""
+        if not hasattr(self, "_dn"):
+            self._dn = abi.Stream()
+            self._ev_step, self._ev_dn = abi.Event(), abi.Event()
+        ph = packed_host
+
+        def up(name):
+            if ph is not None:
+                self.upload_packed(name, ph[name])
+            else:
+                self.upload_field(name, getattr(f, name))
+
+        st = 0
+        for name in ("hnode", "hnode_new"):
+            up(name)
+        first = [k for k in self.STEP_INPUTS if k not in self.STEP_RESULTS and k not in ("hnode", "hnode_new")]
+        for k in range(tracers):
+            for name in first:
+                up(name)
+            if k > 0:
+                self.stream.wait(self._ev_dn)
+            for name in self.STEP_RESULTS:
+                up(name)
+            st = self.step(f, mode=mode, halo=halo, sync=False)
+            self._ev_step.record(self.stream)
+            self._dn.wait(self._ev_step)
+            for name in self.STEP_RESULTS:
+                if ph is not None:
+                    self.download_packed(name, ph["out_" + name], stream=self._dn)
+                else:
+                    stt = C.c_int()
+                    self.lib.fct_ale_field_download_(C.byref(self.h), ci(abi.FIELD_IDS[name]), ci(0),
+                                                     dptr(getattr(out, name).reshape(-1)), self._dn.ref, C.byref(stt))
+                    if stt.value != 0:
+                        raise abi.AbiError(f"download of {name} failed")
             self._ev_dn.record(self._dn)
         self._dn.sync()
         self.stream.sync()

@@ -266,6 +266,51 @@ def build_mesh(tri: np.ndarray, nlev_e: np.ndarray, nl: int, N: int, xy=None,
                 edge_tri=np.ascontiguousarray(edge_tri, dtype=np.int32), xy=xy)
 
 
+def make_delaunay_mesh(n_points: int, nl: int, seed: int = 0, land: bool = True) -> Mesh:
+    """UNSTRUCTURED triangulation: Delaunay of jittered-random points in the unit square (node degrees
+    3..12 instead of the 4 / 8 of the criss-cross grids), optional land blobs, the same bathymetry and
+    Hilbert renumbering as make_mesh.  The irregular counterpart of the structured workloads: ragged
+    per-node edge lists, tiles of uneven size, irregular halos once partitioned."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    # blue-noise-ish: one point per cell of a sqrt(n) grid, jittered by up to 0.45 of a cell, plus 15 % fully random points
+    g = max(2, int(np.sqrt(n_points * 0.85)))
+    ii, jj = np.meshgrid(np.arange(g), np.arange(g), indexing="xy")
+    pts = np.stack([(ii.ravel() + 0.5 + rng.uniform(-0.45, 0.45, g * g)) / g,
+                    (jj.ravel() + 0.5 + rng.uniform(-0.45, 0.45, g * g)) / g], 1)
+    extra = max(0, n_points - g * g)
+    pts = np.concatenate([pts, rng.uniform(0.0, 1.0, (extra, 2))])
+    tri = Delaunay(pts).simplices.astype(np.int64)
+    # drop the sliver triangles of the convex hull (needle-shaped, degenerate areas)
+    a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+    area2 = np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
+    longest = np.maximum.reduce([np.linalg.norm(b - a, axis=1), np.linalg.norm(c - b, axis=1), np.linalg.norm(a - c, axis=1)])
+    keep = area2 > 0.05 * longest ** 2
+    cx, cy = pts[tri].mean(1).T
+    if land:
+        for _ in range(5):
+            bx, by = rng.uniform(0.15, 0.85, 2)
+            ra, rb = rng.uniform(0.02, 0.07, 2)
+            th = rng.uniform(0, np.pi)
+            ux = (cx - bx) * np.cos(th) + (cy - by) * np.sin(th)
+            uy = -(cx - bx) * np.sin(th) + (cy - by) * np.cos(th)
+            keep &= (ux / ra) ** 2 + (uy / rb) ** 2 > 1.0
+    tri, cx, cy = tri[keep], cx[keep], cy[keep]
+    used = np.zeros(pts.shape[0], dtype=bool)
+    used[tri.ravel()] = True
+    old_ids = np.flatnonzero(used)
+    k = 16
+    q = np.minimum((pts[old_ids] * (1 << k)).astype(np.int64), (1 << k) - 1)
+    perm = np.argsort(hilbert_index(q[:, 0], q[:, 1], k), kind="stable")
+    new_of_old = np.full(pts.shape[0], -1, dtype=np.int64)
+    new_of_old[old_ids[perm]] = np.arange(old_ids.size)
+    tri = new_of_old[tri]
+    eorder = np.lexsort((tri.sum(1), tri.min(1)))
+    tri, cx, cy = tri[eorder], cx[eorder], cy[eorder]
+    nlev_e = np.clip(np.rint(3 + _bathymetry(cx, cy) * (nl - 3)), 3, nl).astype(np.int32)
+    return build_mesh(tri, nlev_e, nl, old_ids.size, xy=pts[old_ids[perm]])
+
+
 def make_workload(name: str, seed: int = 0) -> Mesh:
     w = WORKLOADS[name]
     return make_mesh(w["nx"], w["ny"], w["nl"], seed=seed)
@@ -380,12 +425,44 @@ def partition_bounds(mesh: Mesh, nparts: int) -> np.ndarray:
     return np.concatenate([[0], cuts, [mesh.myDim_nod2D]]).astype(np.int64)
 
 
-def partition_mesh(mesh: Mesh, nparts: int, ranks: Optional[List[int]] = None) -> List[Partition]:
+def grow_partition(mesh: Mesh, nparts: int, seed: int = 0) -> np.ndarray:
+    """Greedy graph growing (the initial-partitioning heuristic of METIS-style k-way partitioners): part r
+    grows breadth-first over the node graph from a peripheral seed until it holds 1/nparts of the
+    active node-levels; what is left (possibly several disconnected pieces) joins the last part.  The
+    parts are NOT runs of the node numbering: ragged boundaries, uneven halos, several peers per part."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import breadth_first_order
+    N = mesh.myDim_nod2D
+    e = mesh.edges.astype(np.int64) - 1
+    adj = coo_matrix((np.ones(2 * e.shape[0], np.int8), (np.r_[e[:, 0], e[:, 1]], np.r_[e[:, 1], e[:, 0]])), shape=(N, N)).tocsr()
+    w = mesh.nlevels_nod2D[:N].astype(np.int64) - 1
+    target = w.sum() / nparts
+    owner = np.full(N, -1, np.int32)
+    rng = np.random.default_rng(seed)
+    for r in range(nparts - 1):
+        free = np.flatnonzero(owner < 0)
+        sub = adj[free][:, free]
+        # peripheral seed: the last node of a breadth-first sweep from a random free node
+        start = int(rng.integers(free.size))
+        order = breadth_first_order(sub, start, directed=False, return_predecessors=False)
+        order = breadth_first_order(sub, int(order[-1]), directed=False, return_predecessors=False)
+        cum = np.cumsum(w[free[order]])
+        take = int(np.searchsorted(cum, target)) + 1
+        owner[free[order[:take]]] = r
+    owner[owner < 0] = nparts - 1
+    return owner
+
+
+def partition_mesh(mesh: Mesh, nparts: int, ranks: Optional[List[int]] = None, owner: Optional[np.ndarray] = None) -> List[Partition]:
+    """owner: int32 [N] owning part of every node (e.g. grow_partition); default: contiguous runs of the
+    space-filling-curve numbering, balanced on active node-levels."""
     if mesh.eDim_nod2D:
         raise ValueError("partition a single-domain mesh")
     N = mesh.myDim_nod2D
-    bounds = partition_bounds(mesh, nparts)
-    owner = (np.searchsorted(bounds, np.arange(N), side="right") - 1).astype(np.int32)
+    if owner is None:
+        bounds = partition_bounds(mesh, nparts)
+        owner = (np.searchsorted(bounds, np.arange(N), side="right") - 1).astype(np.int32)
+    owner = np.ascontiguousarray(owner, dtype=np.int32)
     tri = mesh.elem2D_nodes.astype(np.int64) - 1
     edg = mesh.edges.astype(np.int64) - 1
     parts = []
@@ -403,11 +480,11 @@ def partition_mesh(mesh: Mesh, nparts: int, ranks: Optional[List[int]] = None) -
         return halo_gids[r]
 
     for r in wanted:
-        lo, hi = int(bounds[r]), int(bounds[r + 1])
-        n_own = hi - lo
+        own_g = np.flatnonzero(owner == r)          # ascending global ids: the local order of the owned nodes
+        n_own = own_g.size
         hg = halo_of(r)
         H = hg.size
-        gids = np.concatenate([np.arange(lo, hi), hg])
+        gids = np.concatenate([own_g, hg])
         loc = np.full(N, -1, dtype=np.int64)
         loc[gids] = np.arange(gids.size)
         emask = (tri_owner == r).any(1)
@@ -447,7 +524,7 @@ def partition_mesh(mesh: Mesh, nparts: int, ranks: Optional[List[int]] = None) -
             hp = halo_of(p)
             mine = hp[owner[hp] == r]
             if mine.size:
-                send[int(p)] = (mine - lo).astype(np.int32)
+                send[int(p)] = loc[mine].astype(np.int32)
         nb = np.zeros(n_own, dtype=bool)
         le = lm.edges.astype(np.int64) - 1
         cut = (le >= n_own).any(1)

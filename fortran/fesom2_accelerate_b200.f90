@@ -175,6 +175,32 @@ module fesom2_accelerate_b200
       type(c_ptr) :: fields, halo, stream
       integer(c_int) :: istat
     end subroutine
+    ! host arrays already in the packed level storage: one contiguous copy, no repack
+    subroutine fct_ale_plan_packed_size(plan, node_doubles, edge_doubles, istat) bind(C, name="fct_ale_plan_packed_size_")
+      import :: c_int, c_long_long, c_ptr
+      type(c_ptr) :: plan
+      integer(c_long_long) :: node_doubles, edge_doubles
+      integer(c_int) :: istat
+    end subroutine
+    subroutine fct_ale_plan_packed_columns(plan, kind, columns, istat) bind(C, name="fct_ale_plan_packed_columns_")
+      import :: c_int, c_ptr
+      type(c_ptr) :: plan
+      integer(c_int) :: kind, columns(*), istat
+    end subroutine
+    subroutine fct_ale_field_upload_packed(fields, field, tracer, host_packed, stream, istat) &
+                                           bind(C, name="fct_ale_field_upload_packed_")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr) :: fields, stream
+      integer(c_int) :: field, tracer, istat
+      real(c_double) :: host_packed(*)
+    end subroutine
+    subroutine fct_ale_field_download_packed(fields, field, tracer, host_packed, stream, istat) &
+                                             bind(C, name="fct_ale_field_download_packed_")
+      import :: c_int, c_double, c_ptr
+      type(c_ptr) :: fields, stream
+      integer(c_int) :: field, tracer, istat
+      real(c_double) :: host_packed(*)
+    end subroutine
     ! device time (ms) of the exchange inside the last overlapped step that used this halo
     subroutine fct_ale_halo_comm_ms(halo, ms, istat) bind(C, name="fct_ale_halo_comm_ms_")
       import :: c_int, c_double, c_ptr

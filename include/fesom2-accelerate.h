@@ -245,6 +245,21 @@ void fct_ale_field_upload_(void **fields, int *field, int *tracer, real_type *ho
 void fct_ale_field_download_(void **fields, int *field, int *tracer, real_type *host, void **stream,
                              int *istat);
 
+/* Host arrays ALREADY in the packed level storage (fields of fct_ale_fields_create_packed_ only): a caller
+ * that keeps its columns packed moves one contiguous block per array, no staging buffer, no repack kernel,
+ * and only the slots that exist cross the link (about 70 % of the dense array).  Layout of a packed host
+ * array: row r (node or edge) owns the doubles [col[r], col[r+1]) with col from
+ * fct_ale_plan_packed_columns_ (*kind 0: nodes, [myDim_nod2D + eDim_nod2D + 1] entries; 1: edges,
+ * [myDim_edge2D + 1]); level z of the row is element col[r] + z; the total length is
+ * fct_ale_plan_packed_size_.  Node rows hold nlevels-1 active levels plus the bottom interface, rounded up
+ * to an even count; edge rows their active levels rounded up to even. */
+void fct_ale_plan_packed_size_(void **plan, long long *node_doubles, long long *edge_doubles, int *istat);
+void fct_ale_plan_packed_columns_(void **plan, int *kind, unsigned *columns, int *istat);
+void fct_ale_field_upload_packed_(void **fields, int *field, int *tracer, real_type *host_packed, void **stream,
+                                  int *istat);
+void fct_ale_field_download_packed_(void **fields, int *field, int *tracer, real_type *host_packed, void **stream,
+                                    int *istat);
+
 /* bytes that cross the host link when `field` is uploaded from (*upload != 0) or downloaded to
  * `host`: the dense array, or only the slots of the packed storage on the direct path */
 void fct_ale_field_link_bytes_(void **fields, int *field, real_type *host, int *upload, long long *bytes);

@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     abi.load().set_mpi_rank_(abi.ci(int(os.environ.get("LOCAL_RANK", rank))), abi.ci(world))
-    m = mesh_mod.make_workload(name)
+    # "delaunay": an unstructured triangulation cut by greedy graph growing (irregular parts, ragged halos)
+    m = mesh_mod.make_delaunay_mesh(30000, 48, seed=1) if name == "delaunay" else mesh_mod.make_workload(name)
     T = 2
     fs = [mesh_mod.make_fields(m, seed=1 + t) for t in range(T)]
     for k in ("area", "area_inv", "hnode", "hnode_new"):
@@ -37,7 +38,8 @@ def main():
         w = f.copy()
         oracle.fct_ale(m, w)
         wants.append(w)
-    part = mesh_mod.partition_mesh(m, world, ranks=[rank])[0]
+    owner = mesh_mod.grow_partition(m, world, seed=3) if name == "delaunay" else None
+    part = mesh_mod.partition_mesh(m, world, ranks=[rank], owner=owner)[0]
     plan = harness.DevicePlan(part.mesh)
     uid = comm.broadcast_bytes(harness.HaloLink.unique_id() if rank == 0 else None)
     halo = harness.HaloLink(plan, part, uid)

@@ -20,7 +20,7 @@ def gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("name", ["pi", "core2"])
+@pytest.mark.parametrize("name", ["pi", "core2", "delaunay"])
 def test_multi_gpu_step_matches_single_domain_oracle(tmp_path, name):
     n = min(gpu_count(), 4)
     if n < 2:

@@ -26,6 +26,9 @@ def check(got, want, keys=OUT_KEYS, exact=True, owned=None):
 
 
 def cases(mesh_mod, name):
+    if name == "delaunay":    # unstructured: node degrees 2..11, ragged edge lists, land holes; CORE2-size column depths
+        m = mesh_mod.make_delaunay_mesh(30000, 48, seed=1)
+        return m, mesh_mod.make_fields(m, seed=9)
     if name == "deep":        # DART-depth columns: 40 level pairs, cut across warp items with ghost slots
         m = mesh_mod.make_mesh(48, 37, 80, seed=3)
         return m, mesh_mod.make_fields(m, seed=4)
@@ -107,7 +110,7 @@ def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, kno
             abi.tune(k, v)
 
 
-@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "deep"])
+@pytest.mark.parametrize("name", ["tiny", "pi", "core2", "deep", "delaunay"])
 def test_packed_level_storage(mesh_mod, harness, oracle_mod, name):
     """The fast path's own layout: columns hold their active levels only, back to back."""
     m, f = cases(mesh_mod, name)
@@ -499,16 +502,19 @@ def test_step_is_repeatable_and_deterministic(mesh_mod, harness):
 
 
 @pytest.mark.parametrize("nparts,tiled,name", [(n, t, "pi") for n in (2, 5) for t in (False, True, "warp", "packed")] +
-                         [(3, "packed", "deep"), (3, "warp", "deep")])
+                         [(3, "packed", "deep"), (3, "warp", "deep"), (4, "packed", "delaunay"), (6, "packed", "delaunay-grown")])
 def test_partitioned_on_one_gpu(mesh_mod, harness, oracle_mod, nparts, tiled, name):
     """Every partition of a mesh run on this GPU with the halo exchange emulated through the host:
     owned results of all partitions must reproduce the single-domain oracle bit for bit (boundary /
     interior node lists and their tiles, halo numbering, cut edges duplicated on both sides).  "deep":
     nl = 80 columns, where the packed layout runs the two-stage ring with the copy lists ahead."""
-    m, f = cases(mesh_mod, name)
+    m, f = cases(mesh_mod, name.split("-")[0])
     want = f.copy()
     oracle_mod.fct_ale(m, want)
-    parts = mesh_mod.partition_mesh(m, nparts)
+    # "-grown": an irregular partition (greedy graph growing: ragged boundaries, uneven halos, parts that
+    # are not runs of the node numbering) of the unstructured mesh
+    owner = mesh_mod.grow_partition(m, nparts, seed=3) if name.endswith("-grown") else None
+    parts = mesh_mod.partition_mesh(m, nparts, owner=owner)
     plans = [harness.DevicePlan(p.mesh) for p in parts]
     lfs = [mesh_mod.slice_fields(f, p) for p in parts]
     dfs = [harness.DeviceFields(pl, 1, with_uv=False, packed=(tiled == "packed")) for pl in plans]
@@ -605,4 +611,81 @@ def test_benchmark_scale_mesh_against_the_full_oracle(mesh_mod, harness, abi, or
         assert df.step(f, mode=1) == 10
         check(df.download(f, mode=1), want)
     df.free()
+    plan.free()
+
+
+@pytest.mark.parametrize("name", ["pi", "deep"])
+def test_packed_host_arrays(mesh_mod, harness, oracle_mod, name):
+    """A caller that keeps its columns in the packed level storage on the HOST: one contiguous copy per
+    array (fct_ale_field_upload_packed_ / _download_packed_), no repack kernel; same results."""
+    m, f = cases(mesh_mod, name)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, packed=True)
+    names = ["ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "del_ttf_advvert", "del_ttf_advhoriz", "area", "area_inv", "hnode",
+             "hnode_new", "fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus"]
+    for k in names:
+        kind = "edge" if k == "fct_adf_h" else "node"
+        ph = plan.pack_host(getattr(f, k), kind)
+        assert ph.size == plan.packed_columns(kind)[-1]
+        df.upload_packed(k, ph)
+    df.upload_packed("fct_adf_h_out", plan.pack_host(f.fct_adf_h, "edge"))
+    df.upload_packed("fct_adf_v_out", plan.pack_host(f.fct_adf_v, "node"))
+    assert df.step(f, mode=1) == 10
+    got = f.copy()
+    for k, src in (("fct_ttf_max", None), ("fct_ttf_min", None), ("fct_plus", None), ("fct_minus", None),
+                   ("del_ttf_advvert", None), ("del_ttf_advhoriz", None), ("fct_adf_v", "fct_adf_v_out"), ("fct_adf_h", "fct_adf_h_out")):
+        kind = "edge" if k == "fct_adf_h" else "node"
+        ph = np.empty(int(plan.packed_columns(kind)[-1]))
+        df.download_packed(src or k, ph)
+        df.stream.sync()
+        plan.unpack_host(ph, getattr(got, k), kind)
+    check(got, want)
+    # a dense upload and a packed upload of the same array leave the same device image
+    a, b = np.empty(int(plan.packed_columns("node")[-1])), np.empty(int(plan.packed_columns("node")[-1]))
+    df.upload_field("ttf", f.ttf)
+    df.download_packed("ttf", a)
+    df.upload_packed("ttf", plan.pack_host(f.ttf, "node"))
+    df.download_packed("ttf", b)
+    df.stream.sync()
+    assert np.array_equal(a, b)
+    # padded fields refuse packed host copies
+    dd = harness.DeviceFields(plan, 1, with_uv=False)
+    with pytest.raises(Exception):
+        dd.upload_packed("ttf", a)
+    dd.free()
+    df.free()
+    plan.free()
+
+
+def test_host_resident_time_step_batch(mesh_mod, harness, oracle_mod):
+    """host_steps_batch: the mesh-static inputs of a time step uploaded once, the per-tracer inputs per
+    tracer (here the same tracer every time): the tendencies accumulate exactly like repeated steps."""
+    m, f = cases(mesh_mod, "pi")
+    want = f.copy()
+    for _ in range(3):
+        w2 = want.copy()
+        oracle_mod.fct_ale(m, w2)
+        want.del_ttf_advvert, want.del_ttf_advhoriz = w2.del_ttf_advvert, w2.del_ttf_advhoriz
+    plan = harness.DevicePlan(m)
+    for packed_host in (False, True):
+        df = harness.DeviceFields(plan, 1, packed=True)
+        df.upload(f)
+        g = f.copy()
+        ph = None
+        if packed_host:
+            ph = {k: plan.pack_host(getattr(g, k), "edge" if k == "fct_adf_h" else "node") for k in df.STEP_INPUTS}
+            for k in df.STEP_RESULTS:
+                ph["out_" + k] = ph[k]          # results land where the next tracer's inputs are read from
+        for _ in range(3):
+            # each "tracer" continues from the tendencies the previous one produced (g is both input and output)
+            assert df.host_steps_batch(g, g, 1, packed_host=ph) == 10
+        if packed_host:
+            for k in df.STEP_RESULTS:
+                plan.unpack_host(ph[k], getattr(g, k), "node")
+        act = np.arange(m.L)[None, :] < (m.nlevels_nod2D[:, None] - 1)
+        for k in df.STEP_RESULTS:
+            assert np.array_equal(getattr(g, k)[act], getattr(want, k)[act]), (packed_host, k)
+        df.free()
     plan.free()

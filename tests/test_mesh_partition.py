@@ -174,3 +174,45 @@ def test_partitioned_iterative_branch_equals_single_domain(mesh_mod, oracle_mod,
                   "del_ttf_advhoriz"):
             assert bits_equal(getattr(lf, k)[:n], getattr(want, k)[g]), (p.rank, k)
         assert bits_equal(lf.fct_adf_h, want.fct_adf_h[p.mesh.edge_gid]), p.rank
+
+
+def test_graph_grown_partition_of_an_unstructured_mesh_equals_single_domain(mesh_mod, oracle_mod):
+    """Irregular partition (greedy graph growing: parts are not runs of the node numbering, ragged
+    boundaries, uneven halos) of an unstructured Delaunay mesh: oracle pre_comm per part, host exchange
+    of fct_plus / fct_minus, oracle post_comm -- owned results bit-identical to the single domain, and
+    the plan's halo contract holds (send nodes = owned nodes with a halo neighbour, receive ranges
+    inside the halo rows, no edge between two halo nodes)."""
+    m = mesh_mod.make_delaunay_mesh(6000, 30, seed=1)
+    f = mesh_mod.make_fields(m, seed=5)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    owner = mesh_mod.grow_partition(m, 5, seed=2)
+    assert not np.all(np.diff(owner) >= 0)                 # not contiguous runs of the numbering
+    parts = mesh_mod.partition_mesh(m, 5, owner=owner)
+    assert sum(p.mesh.myDim_nod2D for p in parts) == m.myDim_nod2D
+    lfs = [mesh_mod.slice_fields(f, p) for p in parts]
+    for p, lf in zip(parts, lfs):
+        oracle_mod.pre_comm(p.mesh, lf)
+    for p, lf in zip(parts, lfs):
+        n, H = p.mesh.myDim_nod2D, p.mesh.eDim_nod2D
+        le = p.mesh.edges.astype(np.int64) - 1
+        assert ((le < n).any(1)).all()                     # every local edge touches an owned node
+        bnd = np.zeros(n, bool)
+        cut = (le >= n).any(1)
+        ends = le[cut].ravel()
+        bnd[ends[ends < n]] = True
+        for peer, nodes in p.send_lists.items():
+            assert bnd[nodes].all()
+        for peer, (first, cnt) in p.recv_ranges.items():
+            assert n <= first and first + cnt <= n + H
+            nodes = parts[peer].send_lists[p.rank]
+            assert nodes.size == cnt
+            for k in ("fct_plus", "fct_minus"):
+                getattr(lf, k)[first:first + cnt] = getattr(lfs[peer], k)[nodes]
+    for p, lf in zip(parts, lfs):
+        oracle_mod.post_comm(p.mesh, lf)
+        n = p.mesh.myDim_nod2D
+        g = p.mesh.node_gid[:n]
+        for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "del_ttf_advvert", "del_ttf_advhoriz"):
+            assert np.array_equal(getattr(lf, k)[:n], getattr(want, k)[g]), k
+        assert np.array_equal(lf.fct_adf_h, want.fct_adf_h[p.mesh.edge_gid])

@@ -470,3 +470,36 @@ def test_partitioned_tables(mesh_mod, abi, oracle_mod):
             gplus[p.mesh.node_gid[own]] = pl[own]
             gminus[p.mesh.node_gid[own]] = mi[own]
     assert bits_equal(gplus, want.fct_plus) and bits_equal(gminus, want.fct_minus)
+
+
+def test_an_edge_between_two_halo_nodes_is_refused(abi, mesh_mod):
+    """myDim_edge2D holds the edges that touch an owned node; an edge joining two halo
+    nodes would have no node to store its limited flux in the fused phase B (the staged b3h limits
+    every edge): the inspector refuses such a mesh instead of returning stale fluxes for it."""
+    gm = mesh_mod.make_workload("pi")
+    part = mesh_mod.partition_mesh(gm, 3, ranks=[1])[0]
+    m = part.mesh
+    assert inspect(abi, m, packed=1)[0] == 0
+    n = m.myDim_nod2D
+    e = m.edges.copy()
+    # re-point one local edge at two halo nodes
+    e[0] = (n + 1, n + 2)
+    bad = mesh_mod.Mesh(**{**m.__dict__, "edges": np.ascontiguousarray(e)})
+    assert inspect(abi, bad, packed=1)[0] == 1
+
+
+@pytest.mark.parametrize("tn,cap", [(96, 74 * 1024), (9, 24 * 1024)])
+def test_unstructured_delaunay_mesh_packed(mesh_mod, abi, oracle_mod, tn, cap):
+    """An UNSTRUCTURED triangulation (Delaunay of jittered-random points: node degrees 2..11 instead of
+    the 4 / 8 of the criss-cross grids, ragged edge lists, land holes) through the packed tables."""
+    m = mesh_mod.make_delaunay_mesh(700, 21, seed=3)
+    deg = np.bincount((m.edges - 1).ravel(), minlength=m.myDim_nod2D)
+    assert deg.min() <= 3 and deg.max() >= 9
+    f = mesh_mod.make_fields(m, seed=8)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    st, nt, smem, blob, off = inspect(abi, m, tn, cap, packed=1)
+    assert st == 0 and smem <= cap
+    pk = Packed(m)
+    g, P = emulate(m, f, blob, off, nt, packed=pk)
+    compare_packed(m, f, g, pk, want)

@@ -1,0 +1,63 @@
+"""Interleaved A/B of launch-time knobs of the warp-item kernels on ONE plan (the GPU runs under its power
+cap: only interleaved repeats are comparable), with a bit-for-bit check of every configuration's outputs
+against the first one's.
+usage: ab_knobs.py NXxNYxNL "WT_REGS=0;WT_REGS=80;WT_REGS=80,WT_ISSUERS=3" [rounds]"""
+import importlib, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+mesh = importlib.import_module("fesom2-accelerate_b200.mesh")
+harness = importlib.import_module("fesom2-accelerate_b200.harness")
+abi = importlib.import_module("fesom2-accelerate_b200.abi")
+
+nx, ny, nl = [int(x) for x in sys.argv[1].split("x")]
+cfgs = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in c.split(",") if kv) for c in sys.argv[2].split(";")]
+rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+allk = sorted({k for c in cfgs for k in c})
+DEFAULTS = {"WT_REGS": 0, "WT_OPT": -1, "WT_ISSUERS": 0, "WT_WARPS_A": 0, "WT_WARPS_B": 0}
+m = mesh.make_mesh(nx, ny, nl)
+f = mesh.fast_fields(m) if m.myDim_nod2D > 500000 else mesh.make_fields(m, with_uv=False, poison=False)
+Sn, Sg = m.S_n(), m.S_g()
+algA, algB = 8 * (8 * Sn + Sg) + 16 * m.myDim_nod2D, 8 * (13 * Sn + 2 * Sg)
+print(f"N={m.myDim_nod2D} nl={nl} S_n={Sn} S_g={Sg}", flush=True)
+abi.tune("VERBOSE", 1)
+plan = harness.DevicePlan(m)
+df = harness.DeviceFields(plan, 1, with_uv=False, packed=True)
+e0, e1 = abi.Event(), abi.Event()
+
+
+def apply(c):
+    for k in allk:
+        abi.tune(k, c.get(k, DEFAULTS.get(k, 0)))
+
+
+ref = None
+for c in cfgs:
+    apply(c)
+    df.upload(f, outputs=True)
+    assert df.step(f, mode=1) == 10
+    got = df.download(f, mode=1)
+    outs = [getattr(got, k) for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "fct_adf_h", "del_ttf_advvert", "del_ttf_advhoriz")]
+    if ref is None:
+        ref = outs
+    else:
+        same = all(np.array_equal(a, b) for a, b in zip(outs, ref))
+        print(f"cfg {c}: outputs identical to cfg 0: {same}", flush=True)
+        assert same
+tot = [[0.0, 0.0] for _ in cfgs]
+for r in range(rounds + 1):
+    for i, c in enumerate(cfgs):
+        apply(c)
+        res = []
+        for stage in ("phaseA_warp", "phaseB_warp"):
+            for _ in range(3): df.stage(stage, f, sync=False)
+            df.stream.sync(); e0.record(df.stream)
+            for _ in range(10): df.stage(stage, f, sync=False)
+            e1.record(df.stream)
+            res.append(e1.ms_since(e0) / 10)
+        if r > 0:       # round 0 warms the GPU up
+            tot[i][0] += res[0]; tot[i][1] += res[1]
+        print(f"round {r} cfg {i}: phase A {res[0]*1e3:8.1f} us ({algA/res[0]/1e6/65.472:5.1f}%)  phase B {res[1]*1e3:8.1f} us ({algB/res[1]/1e6/65.472:5.1f}%)", flush=True)
+for i, c in enumerate(cfgs):
+    a, b = tot[i][0] / rounds, tot[i][1] / rounds
+    print(f"cfg {i} {c}: phase A {a*1e3:.1f} us ({algA/a/1e6/65.472:.1f}%), phase B {b*1e3:.1f} us ({algB/b/1e6/65.472:.1f}%), step {(a+b)*1e3:.1f} us ({(algA+algB)/(a+b)/1e6/65.472:.1f}%)")
