@@ -30,7 +30,7 @@ SYMBOLS = [
     "fct_ale_field_download_", "fct_ale_field_link_bytes_", "fct_ale_step_", "fct_ale_step_general_", "fct_ale_halo_exchange_field_",
     "stress2rhs_plan_create_", "stress2rhs_plan_destroy_", "stress2rhs_acc_", "stress2rhs_", "fct_ale_stage_",
     "fct_ale_comm_unique_id_", "fct_ale_halo_create_", "fct_ale_halo_destroy_",
-    "fct_ale_halo_exchange_", "fct_ale_halo_comm_ms_",
+    "fct_ale_halo_exchange_", "fct_ale_halo_comm_ms_", "fct_ale_trace_read_",
     "fct_ale_plan_packed_size_", "fct_ale_plan_packed_columns_", "fct_ale_field_upload_packed_", "fct_ale_field_download_packed_",
 ]
 

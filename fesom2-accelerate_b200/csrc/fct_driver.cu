@@ -389,12 +389,15 @@ static int device_sms()
     return n;
 }
 
+static long long *g_trace = nullptr;   // knob WT_TRACE (single device, profiling runs only)
+
 typedef void (*warp_kern_t)(Arrays, WarpTilesDev, int, int, int *);
 struct WarpVariant {
     warp_kern_t fn;
     bool phase_a;
     int stages, consumers, issuers;
     int regs = 0;   // > 0: roles re-allocate registers (setmaxnreg): 4 producer warps + consumers at `regs` each
+    int conv = 2;   // phase A: dedicated converter warps; 0: the consumer warps convert (pipeline v2)
 };
 // total warps (1 fetcher + issuers + [converter] + consumers) a multiple of 4: see fct_warp_kernels.cuh
 #define WT_VA(S, C, I) {k_phase_warp<true, S, C, I>, true, S, C, I}
@@ -402,7 +405,20 @@ struct WarpVariant {
 // register re-allocation between the roles: one producer warpgroup, whole consumer warpgroups
 #define WT_RA(S, C, I, R) {k_phase_warp<true, S, C, I, true, false, R>, true, S, C, I, R}
 #define WT_RB(S, C, I, R) {k_phase_warp<false, S, C, I, true, false, R>, false, S, C, I, R}
+// pipeline v2: the consumers convert the landed rows (no converter warps)
+#define WT_A2(S, C, I, R) {k_phase_warp<true, S, C, I, true, false, R, 0>, true, S, C, I, R, 0}
+// four converter warps instead of two (the a1 pass is 2.2 us of a 4 us refill with two, knob WT_TRACE)
+#define WT_A4(S, C, I) {k_phase_warp<true, S, C, I, true, false, 0, 4>, true, S, C, I, 0, 4}
+// 32 warps: two producer warpgroups at 32 registers (fetcher, 4 issuers, 2 or 3 converters) + 24 consumers at 72
+#define WT_A72(S, I, V) {k_phase_warp<true, S, 24, I, true, false, 72, V>, true, S, 24, I, 72, V}
+#define WT_B72(S, I) {k_phase_warp<false, S, 24, I, true, false, 72>, false, S, 24, I, 72}
 static const WarpVariant g_wvariants[] = {
+    WT_A72(2, 4, 2), WT_A72(3, 4, 2), WT_A72(2, 4, 3), WT_A72(3, 4, 3), WT_B72(2, 4), WT_B72(3, 4),
+    WT_A4(2, 15, 4), WT_A4(3, 15, 4), WT_A4(2, 17, 2), WT_A4(3, 17, 2), WT_A4(2, 19, 4), WT_A4(3, 19, 4), WT_A4(4, 17, 2),
+    WT_A2(2, 19, 4, 0), WT_A2(3, 19, 4, 0), WT_A2(2, 21, 2, 0), WT_A2(3, 21, 2, 0),
+    WT_A2(2, 24, 3, 80), WT_A2(3, 24, 3, 80), WT_A2(2, 24, 1, 80), WT_A2(3, 24, 1, 80),
+    WT_A2(2, 24, 3, 0), WT_A2(3, 24, 3, 0), WT_VB(2, 24, 3), WT_VB(3, 24, 3),   // 28 warps at 72 registers, no re-allocation
+    WT_RB(2, 24, 3, 80), WT_RB(3, 24, 3, 80),
     WT_RA(2, 24, 1, 80), WT_RA(3, 24, 1, 80), WT_RA(2, 20, 1, 88), WT_RA(3, 20, 1, 88),
     WT_RB(2, 24, 1, 80), WT_RB(3, 24, 1, 80), WT_RB(2, 20, 1, 88), WT_RB(3, 20, 1, 88),
     WT_VA(3, 17, 4), WT_VA(3, 13, 4), WT_VA(3, 15, 6), WT_VA(3, 9, 4), WT_VA(3, 19, 2),
@@ -464,14 +480,19 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // 20 consumers at 88 (24 warps launched at 80)
     const bool plain = !iter && (!isA || A.vlimit == 1 || A.vlimit == 0);
     int regs = plain ? env_int("FCT_WT_REGS", 0) : 0;
-    if (regs != 0 && regs != 80 && regs != 88) regs = 80;
-    if (regs > 0) {
-        npw = 1;   // one issuer warp: ~40 bulk copies per packed tile are two rounds of its 32 lanes
+    if (regs != 0 && regs != 80 && regs != 88 && regs != 72) regs = 80;
+    // knob WT_CONV (phase A): 2 = two converter warps (round 1), 0 = the consumer warps convert (pipeline v2)
+    int conv = (isA && plain) ? env_int("FCT_WT_CONV", 2) : 2;
+    if (conv != 0 && conv != 4 && conv != 3) conv = 2;
+    if (regs == 72) {
+        npw = 4;
+        nwc = 24;
+    } else if (regs > 0) {
+        npw = npw <= 0 ? ((isA && conv != 0) ? 1 : 3) : npw;   // 4 producer warps: fetcher + issuers (+ 2 converters)
         nwc = nwc <= 0 ? (regs == 80 ? 24 : 20) : nwc;
-        if (T.opt >= 0 && env_int("FCT_WT_OPT", -1) < 0) T.opt |= 1;   // few producers: suspended in hardware, not polling
     } else {
         npw = npw <= 0 ? ((packed && stages != 2) ? 2 : 4) : npw;
-        nwc = nwc <= 0 ? (isA ? 21 - npw : 23 - npw) : nwc;
+        nwc = nwc <= 0 ? (isA ? 23 - conv - npw : 23 - npw) : nwc;
     }
     constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
@@ -481,6 +502,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     int vi = -1, best = 1 << 30;
     for (int i = 0; i < (vl ? NVL : (iter ? NVI : NV1)); ++i) {
         if (table[i].stages != stages || table[i].phase_a != isA || table[i].regs != regs) continue;
+        if (isA && plain && table[i].conv != conv) continue;
         const int dist = 4 * std::abs(table[i].consumers - nwc) + std::abs(table[i].issuers - npw);
         if (dist < best) {
             best = dist;
@@ -493,8 +515,9 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     bool first = false;
     if (!ensure_smem_attr(reinterpret_cast<const void *>(v.fn), smem, &first)) return false;
     if (first && env_int("FCT_VERBOSE", 0))
-        std::fprintf(stderr, "fesom2-accelerate: warp kernel %c: %d stages of %d B, %d consumer + %d issuer warps\n",
-                     isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers);
+        std::fprintf(stderr, "fesom2-accelerate: warp kernel %c: %d stages of %d B, %d consumer + %d issuer%s warps%s, opt %d\n",
+                     isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers, (isA && v.conv) ? (v.conv == 4 ? " + 4 converter" : (v.conv == 3 ? " + 3 converter" : " + 2 converter")) : "",
+                     v.regs > 0 ? ", registers re-allocated" : "", T.opt);
     const int sms = device_sms();
     const long long total = (long long)T.ntiles * ntracers;
     if (total >= (1LL << 30)) {
@@ -523,8 +546,16 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         }
         ctr = ring + 2 * (ctr_next.fetch_add(1) % CTR_SLOTS);
     }
+    // profiling aid (knob WT_TRACE 1 = phase A, 2 = phase B): pipeline time stamps of CTA 0, read back with fct_ale_trace_read_
+    T.trace = nullptr;
+    if (env_int("FCT_WT_TRACE", 0) == (isA ? 1 : 2)) {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (!g_trace && !cuda_ok(cudaMalloc(&g_trace, sizeof(long long) * WT_TRACE_SLOTS * WT_TRACE_ITERS), "cudaMalloc(trace)")) return false;
+        cudaMemsetAsync(g_trace, 0, sizeof(long long) * WT_TRACE_SLOTS * WT_TRACE_ITERS, s);
+        T.trace = g_trace;
+    }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
-    const int warps = v.regs > 0 ? WT_PRODUCER_WARPS + v.consumers : v.issuers + 1 + (isA ? WT_CONVERTERS : 0) + v.consumers;
+    const int warps = v.regs > 0 ? wt_producer_warps(v.regs) + v.consumers : v.issuers + 1 + (isA ? v.conv : 0) + v.consumers;
     v.fn<<<grid, warps * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");
@@ -1285,6 +1316,18 @@ void fct_ale_tune_(const char *name, int *value)
 }
 
 void fct_ale_launch_count_(long long *count) { *count = g_launches.load(); }
+
+void fct_ale_trace_read_(long long *stamps, int *capacity, int *slots, int *istat)
+{
+    *istat = 1;
+    *slots = WT_TRACE_SLOTS;
+    if (!g_trace || !stamps) return;
+    const size_t n = std::min<size_t>((size_t)std::max(*capacity, 0), (size_t)WT_TRACE_SLOTS * WT_TRACE_ITERS);
+    if (!cuda_ok(cudaDeviceSynchronize(), "trace sync") ||
+        !cuda_ok(cudaMemcpy(stamps, g_trace, n * sizeof(long long), cudaMemcpyDeviceToHost), "trace read"))
+        return;
+    *istat = 0;
+}
 
 void fct_ale_device_info_(char *name64, int *cc_major, int *cc_minor, int *sm_count, int *istat)
 {

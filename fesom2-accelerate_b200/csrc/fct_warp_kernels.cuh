@@ -56,9 +56,22 @@ struct WarpTilesDev {
     int diag;                   // timing experiments only (wrong results): 1 skip the edge-row copies, 2 skip all row copies
     int opt;                    // scheduling options (results unaffected): 1 producers wait suspended in hardware
                                 // instead of polling, 2 consumers issue a tile's first loads before waiting for its rows,
-                                // 4 copy lists travel ahead of their blobs (needs max_copies <= WT_PRE_MAX_COPIES)
+                                // 4 copy lists travel ahead of their blobs (needs max_copies <= WT_PRE_MAX_COPIES),
+                                // 8 fetcher and issuers probe a released stage every 40 ns (hand-over on the critical path)
     int max_copies;             // longest copy list of a tile
+    long long *trace;           // profiling aid (knob WT_TRACE): SM-clock stamps of the pipeline events of CTA 0,
+                                // WT_TRACE_SLOTS per tile iteration, at most WT_TRACE_ITERS iterations; null: off
 };
+constexpr int WT_TRACE_SLOTS = 10;
+constexpr int WT_TRACE_ITERS = 4096;
+// slots: 0 fetcher: stage seen empty, 1 fetcher: blob copy issued, 2 issuer: starts the row copies, 3 issuer: copies issued,
+//        4 converter: rows landed, 5 converter: a1 done, 6 first consumer warp: tile ready, 7 first consumer warp: leaves
+//        the tile, 8 last consumer warp: tile ready, 9 last consumer warp: leaves the tile
+__device__ __forceinline__ void wt_trace(const WarpTilesDev &T, int it, int slot)
+{
+    if (T.trace != nullptr && blockIdx.x == 0 && it < WT_TRACE_ITERS && (threadIdx.x & 31) == 0)
+        T.trace[it * WT_TRACE_SLOTS + slot] = clock64();
+}
 
 // warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A WT_CONVERTERS a1 converters, then NWC
 // consumers (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128 per
@@ -139,12 +152,41 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 // producer-side wait: producers are idle most of the time; probe, then sleep between probes so that
 // they leave the issue slots to the consumers (costs a fraction of a microsecond per hand-over)
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, bool suspended = false)
+// the same wait with a short suspend-time hint: one probe per HINT ns instead of one per ~26 ns (the opcode mix of
+// round 1 shows the nanosleep loop below turning over every ~26 ns per producer warp: 15 % of all issued instructions)
+template <int HINT>
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity)
 {
-    if (suspended) {
+    uint32_t done = 0;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "n"(HINT)
+            : "memory");
+    } while (!done);
+}
+// mode (WarpTilesDev::opt): bit 0 suspended with a 20 us hint, bit 4 (16) a 1 us hint, bit 5 (32) a 250 ns hint,
+// bit 6 (64) the polling loop with a 2 us sleep instead of 400 ns
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, int mode = 0)
+{
+    if (mode & 1) {
         mbar_wait(bar, parity);
         return;
     }
+    if (mode & 16) {
+        mbar_wait_hint<1000>(bar, parity);
+        return;
+    }
+    if (mode & 32) {
+        mbar_wait_hint<250>(bar, parity);
+        return;
+    }
+    const unsigned ns = (mode & 64) ? 2000u : (unsigned)WT_IDLE_NS;
     uint32_t done = 0;
     for (;;) {
         asm volatile(
@@ -157,7 +199,28 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, bo
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(WT_IDLE_NS);
+        __nanosleep(ns);
+    }
+}
+
+// wait on the pipeline's critical hand-over (a stage released by its last consumer warp): the refill
+// starts the moment this returns, so the probe interval is short (measured with knob WT_TRACE: the 400 ns
+// sleep left a released stage idle for 0.6 us, the suspended try_wait for 1.6 us, of a 5 us tile period)
+__device__ __forceinline__ void mbar_wait_handover(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(40);
     }
 }
 
@@ -767,8 +830,12 @@ __device__ __forceinline__ void wt_item_b_iter(const Arrays &A, const WtView &V,
 // setmaxnreg moves registers INSIDE the CTA's launch allocation (threads x registers of the compiled
 // kernel): the launch must already own what the roles hold afterwards.  28 warps x 72 registers = 64 512 =
 // 4 producer warps x 24 + 24 consumer warps x 80.
+// With RC == 72 the producer side is TWO warpgroups (fetcher, four issuers, the converters) at 32 registers
+// and the CTA is launched with 32 warps at 64: 8 x 32 x 32 + 24 x 32 x 72 = 63 488 of 65 536.
 constexpr int WT_PRODUCER_WARPS = 4;
 constexpr int WT_PRODUCER_REGS = 24;
+__host__ __device__ constexpr int wt_producer_warps(int rc) { return rc == 72 ? 8 : 4; }
+__host__ __device__ constexpr int wt_producer_regs(int rc) { return rc == 72 ? 32 : 24; }
 template <int N>
 __device__ __forceinline__ void reg_dealloc()
 {
@@ -780,17 +847,24 @@ __device__ __forceinline__ void reg_alloc()
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false, int RC = 0>
-__global__ void __launch_bounds__((RC > 0 ? WT_PRODUCER_WARPS : NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0)) * 32 + NWC * 32, 1)
+// NCV: phase A's a1 pass over the landed rows.  NCV > 0: that many dedicated converter warps (round 1).
+// NCV == 0 (pipeline v2): the pass is cut into WT_CONV_CHUNKS chunks that the CONSUMER warps draw from the
+// tile's item counter ahead of its warp items: the first warps to reach a tile convert it, in parallel and at
+// full issue priority, instead of two converter warps taking 2.2 us of every 4 us refill (WT_TRACE).
+constexpr int WT_CONV_CHUNKS = 16;
+template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false, int RC = 0, int NCV = WT_CONVERTERS>
+__global__ void __launch_bounds__((RC > 0 ? wt_producer_warps(RC) : NPW + 1 + (PHASE_A ? NCV : 0)) * 32 + NWC * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
     extern __shared__ __align__(128) unsigned char wt_sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // first consumer warp
-    constexpr int NPROD = RC > 0 ? WT_PRODUCER_WARPS : NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0);
-    static_assert(RC == 0 || (NPW + 1 + (PHASE_A ? WT_CONVERTERS : 0) <= WT_PRODUCER_WARPS && NWC % 4 == 0 &&
-                              WT_PRODUCER_WARPS * 32 * WT_PRODUCER_REGS + NWC * 32 * RC <=
-                                  (WT_PRODUCER_WARPS + NWC) * 32 * ((65536 / ((WT_PRODUCER_WARPS + NWC) * 32)) & ~7) &&
+    constexpr int NPROD = RC > 0 ? wt_producer_warps(RC) : NPW + 1 + (PHASE_A ? NCV : 0);
+    constexpr int PREGS = wt_producer_regs(RC);
+    constexpr bool CONSUMERS_CONVERT = PHASE_A && NCV == 0;
+    constexpr int NCH = CONSUMERS_CONVERT ? WT_CONV_CHUNKS : 0;   // conversion chunks ahead of a tile's warp items
+    static_assert(RC == 0 || (NPW + 1 + (PHASE_A ? NCV : 0) <= NPROD && NWC % 4 == 0 &&
+                              NPROD * 32 * PREGS + NWC * 32 * RC <= (NPROD + NWC) * 32 * ((65536 / ((NPROD + NWC) * 32)) & ~7) &&
                               RC % 8 == 0),
                   "register budget of the re-allocated roles");
     const uint32_t bar = smem_u32(wt_sm);
@@ -814,7 +888,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             mbar_init(b_empty(s), NWC);
             mbar_init(b_blob(s), 1);
             mbar_init(b_rows(s), 1);
-            mbar_init(b_ready(s), WT_CONVERTERS);
+            mbar_init(b_ready(s), CONSUMERS_CONVERT ? WT_CONV_CHUNKS : (NCV > 0 ? NCV : 1));
             mbar_init(b_pre(s), 1);
             mbar_init(b_prefree(s), NPW);
         }
@@ -822,7 +896,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
     }
     __syncthreads();
     if (RC > 0) {
-        if (warp < WT_PRODUCER_WARPS) reg_dealloc<WT_PRODUCER_REGS>();
+        if (warp < NPROD) reg_dealloc<PREGS>();
         else reg_alloc<(RC > 0 ? RC : 80)>();
     }
 
@@ -845,7 +919,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             }
             if (lists_ahead) {
                 // the copy list goes ahead into its slot as soon as the issuers are done with the slot's last list
-                mbar_wait_idle(b_prefree(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
+                mbar_wait_idle(b_prefree(s), ((it / NSTAGE) & 1) ^ 1, T.opt);
                 if (lane == 0) {
                     if (v < total) {
                         const uint32_t nb = min((b1 - b0) * 16u, (uint32_t)WT_PRE_BYTES);
@@ -858,7 +932,9 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                     }
                 }
             }
-            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
+            if (T.opt & 8) mbar_wait_handover(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+            else mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt);
+            wt_trace(T, it, 0);
             if (v >= total) {
                 if (lane == 0) {
                     tile_of[s] = -1;
@@ -873,6 +949,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 mbar_expect_tx(b_blob(s), (b1 - b0) * 16u);
                 bulk_g2s(smem_u32(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes), T.blob + b0, (b1 - b0) * 16u, b_blob(s));
             }
+            wt_trace(T, it, 1);
             __syncwarp();
         }
         // the last CTA to finish drawing rearms the counter for the next launch
@@ -888,7 +965,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             // list from its own slot: rows pulled into L2 while the stage is still busy, copies issued
             // the moment it is released (next to the blob's copy, not after it)
             const int s = it % NSTAGE;
-            mbar_wait_idle(b_pre(s), (it / NSTAGE) & 1, T.opt & 1);
+            mbar_wait_idle(b_pre(s), (it / NSTAGE) & 1, T.opt);
             const int tr = pre_tracer[s];
             if (tr < 0) break;
             const unsigned char *pl = wt_sm + WT_SMEM_CTRL + s * WT_PRE_BYTES;
@@ -904,7 +981,9 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(sz) : "memory");
             }
-            mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt & 1);
+            if (T.opt & 8) mbar_wait_handover(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
+            else mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt);
+            if (warp == 1) wt_trace(T, it, 2);
             if (warp == 1 && lane == 0) mbar_expect_tx(b_rows(s), (uint32_t)h2.w);
             const uint32_t sa = smem_u32(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes + h2.x);
             for (int u = (warp - 1) * 32 + lane; u < n_copies; u += NPW * 32) {
@@ -914,14 +993,16 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 bulk_g2s(sa + so, src, sz, b_rows(s));
             }
+            if (warp == 1) wt_trace(T, it, 3);
             __syncwarp();
             if (lane == 0) mbar_arrive(b_prefree(s));
         }
         for (int it = 0; !lists_ahead; ++it) {
             const int s = it % NSTAGE;
-            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt & 1);
+            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt);
             if (tile_of[s] < 0) break;
             const int tr = tracer_of[s];
+            if (warp == 1) wt_trace(T, it, 2);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             // the transaction count may run negative until this arrives; the phase cannot complete before
             if (warp == 1 && lane == 0)
@@ -937,34 +1018,38 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 if (T.diag == 0 || (T.diag == 1 && arr != 2)) bulk_g2s(sa + so, src, sz, b_rows(s));
             }
+            if (warp == 1) wt_trace(T, it, 3);
             __syncwarp();
         }
-    } else if (PHASE_A && warp <= NPW + WT_CONVERTERS) {
+    } else if (PHASE_A && NCV > 0 && warp <= NPW + NCV) {
         // ---- phase A: a1 in place on the landed rows, (fct_LO, ttf) -> (max, min), reference.cpp:315-316 ----
         const int cl = (warp - NPW - 1) * 32 + lane;   // lane among the converter warps
         for (int it = 0;; ++it) {
             const int s = it % NSTAGE;
-            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt & 1);
+            mbar_wait_idle(b_blob(s), (it / NSTAGE) & 1, T.opt);
             if (tile_of[s] < 0) break;
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
-            mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1, T.opt & 1);
+            mbar_wait_idle(b_rows(s), (it / NSTAGE) & 1, T.opt);
+            if (cl < 32) wt_trace(T, it, 4);
             double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
             const int n16 = V.rows_bytes >> 4;
 #pragma unroll 4
-            for (int g = cl; g < n16; g += 32 * WT_CONVERTERS) {
+            for (int g = cl; g < n16; g += 32 * (NCV > 0 ? NCV : 1)) {
                 const double2 l = pa[g], t = pb[g];
                 pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
                 pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));
             }
             fence_proxy_async();   // the next refill of this stage is written by the async proxy
+            if (cl < 32) wt_trace(T, it, 5);
             __syncwarp();
             if (lane == 0) mbar_arrive(b_ready(s));
         }
     } else if (warp >= NPROD) {
         // ---- consumers ----
+        // (with CONSUMERS_CONVERT the first NCH draws of a tile are its conversion chunks: indices -NCH .. -1)
         auto draw = [&](int s) {   // lane 0 only; broadcast with __shfl_sync when needed
             int wi = 0;
-            if (lane == 0) wi = smem_fetch_add(next_item + s);
+            if (lane == 0) wi = smem_fetch_add(next_item + s) - NCH;
             return wi;
         };
         for (int it = 0;; ++it) {
@@ -973,7 +1058,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             if (tile_of[s] < 0) break;
             const int tr = tracer_of[s];
             const bool first_loads_ahead = T.opt & 2;
-            if (!first_loads_ahead) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            if (!first_loads_ahead && !CONSUMERS_CONVERT) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             const size_t tn = tr * A.ts_node;
             const double *g_v = A.adf_v + tr * A.ts_nodev;
@@ -982,9 +1067,32 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             // item of a tile needs the blob only (schedule + node headers): its loads travel while the
             // warp waits for the tile's rows
             int wi = __shfl_sync(0xffffffffu, draw(s), 0);
+            if (CONSUMERS_CONVERT) {
+                // a1 in place on the landed rows, (fct_LO, ttf) -> (max, min), reference.cpp:315-316: the warps
+                // that reach the tile first take its chunks
+                if (wi < 0) mbar_wait(b_rows(s), (it / NSTAGE) & 1);
+                if (wi < 0 && warp == NPROD) wt_trace(T, it, 4);
+                while (wi < 0) {
+                    double2 *pa = reinterpret_cast<double2 *>(V.rowsA), *pb = reinterpret_cast<double2 *>(V.rowsB);
+                    const int n16 = V.rows_bytes >> 4, per = (n16 + NCH - 1) / (NCH > 0 ? NCH : 1);
+                    const int g0 = (wi + NCH) * per, g1 = min(g0 + per, n16);
+#pragma unroll 4
+                    for (int g = g0 + lane; g < g1; g += 32) {
+                        const double2 l = pa[g], t = pb[g];
+                        pa[g] = make_double2(pick_max(l.x, t.x), pick_max(l.y, t.y));
+                        pb[g] = make_double2(pick_min(l.x, t.x), pick_min(l.y, t.y));
+                    }
+                    fence_proxy_async();   // the next refill of this stage is written by the async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_ready(s));
+                    wi = __shfl_sync(0xffffffffu, draw(s), 0);
+                }
+            }
             WtEarly E;
             if (wi < V.n_witems) E = wt_early<PHASE_A, ITER>(A, V, wi, lane, g_v, tn);
-            if (first_loads_ahead) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            if (first_loads_ahead || CONSUMERS_CONVERT) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            if (warp == NPROD) wt_trace(T, it, 6);
+            if (warp == NPROD + NWC - 1) wt_trace(T, it, 8);
             while (wi < V.n_witems) {
                 WtEarly En;
                 int wn = 0;
@@ -998,6 +1106,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 wi = wn;
                 E = En;
             }
+            if (warp == NPROD) wt_trace(T, it, 7);
+            if (warp == NPROD + NWC - 1) wt_trace(T, it, 9);
             __syncwarp();
             if (lane == 0) mbar_arrive(b_empty(s));
         }

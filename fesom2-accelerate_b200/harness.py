@@ -193,7 +193,7 @@ class DevicePlan:
         cols = np.arange(W, dtype=np.int64)[None, :]
         for r in range(0, dense.shape[0], step):
             mask = cols < cnt[r:r + step, None]
-            dst = (col[r:r + step, None] + cols)[mask]
+            dst = (col[:-1][r:r + step, None] + cols)[mask]
             out[dst] = dense[r:r + step][mask]
         return out
 
@@ -205,7 +205,7 @@ class DevicePlan:
         cols = np.arange(W, dtype=np.int64)[None, :]
         for r in range(0, dense.shape[0], step):
             mask = cols < cnt[r:r + step, None]
-            dense[r:r + step][mask] = packed[(col[r:r + step, None] + cols)[mask]]
+            dense[r:r + step][mask] = packed[(col[:-1][r:r + step, None] + cols)[mask]]
         return dense
 
     def free(self):

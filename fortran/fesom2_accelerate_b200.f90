@@ -201,6 +201,11 @@ module fesom2_accelerate_b200
       integer(c_int) :: field, tracer, istat
       real(c_double) :: host_packed(*)
     end subroutine
+    subroutine fct_ale_trace_read(stamps, capacity, slots, istat) bind(C, name="fct_ale_trace_read_")
+      import :: c_int, c_long_long
+      integer(c_long_long) :: stamps(*)
+      integer(c_int) :: capacity, slots, istat
+    end subroutine
     ! device time (ms) of the exchange inside the last overlapped step that used this halo
     subroutine fct_ale_halo_comm_ms(halo, ms, istat) bind(C, name="fct_ale_halo_comm_ms_")
       import :: c_int, c_double, c_ptr

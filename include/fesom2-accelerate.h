@@ -319,6 +319,11 @@ void fct_ale_halo_destroy_(void **halo, int *istat);
  * "HALO_SKIP" 1 runs the same launches WITHOUT the exchange (timing experiment, stale halo rows):
  * step time minus that = the part of the communication the overlap does not hide. */
 void fct_ale_halo_comm_ms_(void **halo, real_type *ms, int *istat);
+/* Profiling aid of the warp-item kernels (tuning knob "WT_TRACE" 1: phase A, 2: phase B): SM-clock stamps of
+ * the pipeline events of CTA 0 of the last traced launch (*slots per tile iteration: stage seen empty, blob
+ * issued, row copies started / issued, rows landed, a1 done, first / last consumer warp enters / leaves the
+ * tile).  tools/trace_pipeline.py turns them into the per-tile refill and compute times. */
+void fct_ale_trace_read_(long long *stamps, int *capacity, int *slots, int *istat);
 /* the exchange alone (tests, timing) */
 void fct_ale_halo_exchange_(void **fields, void **halo, void **stream, int *istat);
 /* exchange_nod of ONE per-tracer node array of width nl-1 (*field: FCT_LO between two passes of

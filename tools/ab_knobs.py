@@ -14,21 +14,32 @@ nx, ny, nl = [int(x) for x in sys.argv[1].split("x")]
 cfgs = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in c.split(",") if kv) for c in sys.argv[2].split(";")]
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 allk = sorted({k for c in cfgs for k in c})
-DEFAULTS = {"WT_REGS": 0, "WT_OPT": -1, "WT_ISSUERS": 0, "WT_WARPS_A": 0, "WT_WARPS_B": 0}
+DEFAULTS = {"WT_REGS": 0, "WT_OPT": -1, "WT_ISSUERS": 0, "WT_WARPS_A": 0, "WT_WARPS_B": 0, "WT_CONV": 2}
 m = mesh.make_mesh(nx, ny, nl)
 f = mesh.fast_fields(m) if m.myDim_nod2D > 500000 else mesh.make_fields(m, with_uv=False, poison=False)
 Sn, Sg = m.S_n(), m.S_g()
 algA, algB = 8 * (8 * Sn + Sg) + 16 * m.myDim_nod2D, 8 * (13 * Sn + 2 * Sg)
 print(f"N={m.myDim_nod2D} nl={nl} S_n={Sn} S_g={Sg}", flush=True)
 abi.tune("VERBOSE", 1)
-plan = harness.DevicePlan(m)
-df = harness.DeviceFields(plan, 1, with_uv=False, packed=True)
+# knobs read when a plan is built (tile size, ring depth): one plan + fields per distinct set
+PLAN_KNOBS = ("WT_STAGES", "WT_NODES", "WT_SMEM")
+plans = {}
+for c in cfgs:
+    key = tuple(c.get(k, 0) for k in PLAN_KNOBS)
+    if key not in plans:
+        for k, v in zip(PLAN_KNOBS, key):
+            abi.tune(k, v)
+        pl = harness.DevicePlan(m)
+        plans[key] = (pl, harness.DeviceFields(pl, 1, with_uv=False, packed=True))
 e0, e1 = abi.Event(), abi.Event()
+df = None
 
 
 def apply(c):
+    global df
     for k in allk:
         abi.tune(k, c.get(k, DEFAULTS.get(k, 0)))
+    df = plans[tuple(c.get(k, 0) for k in PLAN_KNOBS)][1]
 
 
 ref = None
