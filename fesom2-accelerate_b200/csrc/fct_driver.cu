@@ -412,7 +412,11 @@ struct WarpVariant {
 // 32 warps: two producer warpgroups at 32 registers (fetcher, 4 issuers, 2 or 3 converters) + 24 consumers at 72
 #define WT_A72(S, I, V) {k_phase_warp<true, S, 24, I, true, false, 72, V>, true, S, 24, I, 72, V}
 #define WT_B72(S, I) {k_phase_warp<false, S, 24, I, true, false, 72>, false, S, 24, I, 72}
+// the a1 pass folded into the consumers' edge loop: no converter warps, no pass over the staged rows (conv = -1)
+#define WT_AF(S, C, I) {k_phase_warp<true, S, C, I, true, false, 0, -1>, true, S, C, I, 0, -1}
 static const WarpVariant g_wvariants[] = {
+    WT_AF(2, 19, 4), WT_AF(3, 19, 4), WT_AF(2, 21, 2), WT_AF(3, 21, 2), WT_AF(4, 19, 4), WT_AF(4, 21, 2),
+    WT_AF(2, 24, 3), WT_AF(3, 24, 3), WT_AF(2, 23, 4), WT_AF(3, 23, 4),   // 28 warps at 72 registers
     WT_A72(2, 4, 2), WT_A72(3, 4, 2), WT_A72(2, 4, 3), WT_A72(3, 4, 3), WT_B72(2, 4), WT_B72(3, 4),
     WT_A4(2, 15, 4), WT_A4(3, 15, 4), WT_A4(2, 17, 2), WT_A4(3, 17, 2), WT_A4(2, 19, 4), WT_A4(3, 19, 4), WT_A4(4, 17, 2),
     WT_A2(2, 19, 4, 0), WT_A2(3, 19, 4, 0), WT_A2(2, 21, 2, 0), WT_A2(3, 21, 2, 0),
@@ -481,9 +485,12 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     const bool plain = !iter && (!isA || A.vlimit == 1 || A.vlimit == 0);
     int regs = plain ? env_int("FCT_WT_REGS", 0) : 0;
     if (regs != 0 && regs != 80 && regs != 88 && regs != 72) regs = 80;
-    // knob WT_CONV (phase A): 2 = two converter warps (round 1), 0 = the consumer warps convert (pipeline v2)
-    int conv = (isA && plain) ? env_int("FCT_WT_CONV", 2) : 2;
-    if (conv != 0 && conv != 4 && conv != 3) conv = 2;
+    // knob WT_CONV (phase A, vlimit 1): -1 = a1 folded into the edge loop, 2 / 3 / 4 = that many converter warps
+    // (round 1: 2), 0 = the consumer warps run the a1 pass in chunks
+    // default since round 2: -1, the a1 pass folded into the consumers' edge loop (no converter warps, 20 % fewer
+    // shared-memory wavefronts): +7 % on phase A, interleaved, on nl = 48 and nl = 70 (profiles/r2_v10_*)
+    int conv = (isA && plain) ? env_int("FCT_WT_CONV", -1) : 2;
+    if (conv != 0 && conv != 4 && conv != 3 && conv != -1) conv = 2;
     if (regs == 72) {
         npw = 4;
         nwc = 24;
@@ -492,7 +499,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         nwc = nwc <= 0 ? (regs == 80 ? 24 : 20) : nwc;
     } else {
         npw = npw <= 0 ? ((packed && stages != 2) ? 2 : 4) : npw;
-        nwc = nwc <= 0 ? (isA ? 23 - conv - npw : 23 - npw) : nwc;
+        nwc = nwc <= 0 ? (isA ? 23 - std::max(conv, 0) - npw : 23 - npw) : nwc;
     }
     constexpr int NV1 = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
     constexpr int NVL = sizeof(g_wvariants_vl) / sizeof(g_wvariants_vl[0]);
@@ -516,7 +523,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     if (!ensure_smem_attr(reinterpret_cast<const void *>(v.fn), smem, &first)) return false;
     if (first && env_int("FCT_VERBOSE", 0))
         std::fprintf(stderr, "fesom2-accelerate: warp kernel %c: %d stages of %d B, %d consumer + %d issuer%s warps%s, opt %d\n",
-                     isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers, (isA && v.conv) ? (v.conv == 4 ? " + 4 converter" : (v.conv == 3 ? " + 3 converter" : " + 2 converter")) : "",
+                     isA ? 'A' : 'B', stages, stage_bytes, v.consumers, v.issuers, (isA && v.conv > 0) ? (v.conv == 4 ? " + 4 converter" : (v.conv == 3 ? " + 3 converter" : " + 2 converter")) : "",
                      v.regs > 0 ? ", registers re-allocated" : "", T.opt);
     const int sms = device_sms();
     const long long total = (long long)T.ntiles * ntracers;
@@ -555,7 +562,7 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         T.trace = g_trace;
     }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
-    const int warps = v.regs > 0 ? wt_producer_warps(v.regs) + v.consumers : v.issuers + 1 + (isA ? v.conv : 0) + v.consumers;
+    const int warps = v.regs > 0 ? wt_producer_warps(v.regs) + v.consumers : v.issuers + 1 + (isA ? std::max(v.conv, 0) : 0) + v.consumers;
     v.fn<<<grid, warps * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");

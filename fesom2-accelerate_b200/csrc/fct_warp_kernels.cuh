@@ -315,6 +315,59 @@ __device__ __forceinline__ void wt_edge_a(int z0, int meta, const double2 &x, co
         : "r"(z0), "r"(meta), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y), "d"(h.x), "d"(h.y));
 }
 
+// The same edge with the a1 pass folded in (NCV < 0: no converter warps, no pass over the staged rows): x / y are
+// the neighbour's RAW fct_LO / ttf rows and its a1 bounds max(LO, ttf) / min(LO, ttf) (reference.cpp:315-316) are
+// taken on the fly: hi = max(hi, LO, ttf), lw = min(lw, LO, ttf) -- exact, max / min are associative.
+__device__ __forceinline__ void wt_edge_a_fold(int z0, int meta, const double2 &x, const double2 &y, const double2 &h,
+                                               double &hi0, double &hi1, double &lw0, double &lw1, double &p0,
+                                               double &p1, double &m0, double &m1)
+{
+    asm("{\n"
+        ".reg .pred P0, P1, q;\n"
+        ".reg .b32 dg, sh, z1;\n"
+        ".reg .f64 s, a, t, h0, h1;\n"
+        "and.b32 dg, %9, 0xffff;\n"
+        "and.b32 sh, %9, 0x80000000;\n"
+        "or.b32 sh, sh, 0x3FF00000;\n"
+        "mov.b64 s, {0, sh};\n"
+        "add.s32 z1, %8, 1;\n"
+        "setp.lt.s32 P0, %8, dg;\n"
+        "setp.lt.s32 P1, z1, dg;\n"
+        "setp.lt.and.f64 q, %0, %10, P0;\n"
+        "selp.f64 %0, %10, %0, q;\n"
+        "setp.lt.and.f64 q, %0, %12, P0;\n"
+        "selp.f64 %0, %12, %0, q;\n"
+        "setp.lt.and.f64 q, %1, %11, P1;\n"
+        "selp.f64 %1, %11, %1, q;\n"
+        "setp.lt.and.f64 q, %1, %13, P1;\n"
+        "selp.f64 %1, %13, %1, q;\n"
+        "setp.lt.and.f64 q, %10, %2, P0;\n"
+        "selp.f64 %2, %10, %2, q;\n"
+        "setp.lt.and.f64 q, %12, %2, P0;\n"
+        "selp.f64 %2, %12, %2, q;\n"
+        "setp.lt.and.f64 q, %11, %3, P1;\n"
+        "selp.f64 %3, %11, %3, q;\n"
+        "setp.lt.and.f64 q, %13, %3, P1;\n"
+        "selp.f64 %3, %13, %3, q;\n"
+        "selp.f64 h0, %14, 0d0000000000000000, P0;\n"
+        "selp.f64 h1, %15, 0d0000000000000000, P1;\n"
+        "abs.f64 a, h0;\n"
+        "fma.rn.f64 t, h0, s, a;\n"
+        "fma.rn.f64 %4, t, 0d3FE0000000000000, %4;\n"
+        "neg.f64 a, a;\n"
+        "fma.rn.f64 t, h0, s, a;\n"
+        "fma.rn.f64 %6, t, 0d3FE0000000000000, %6;\n"
+        "abs.f64 a, h1;\n"
+        "fma.rn.f64 t, h1, s, a;\n"
+        "fma.rn.f64 %5, t, 0d3FE0000000000000, %5;\n"
+        "neg.f64 a, a;\n"
+        "fma.rn.f64 t, h1, s, a;\n"
+        "fma.rn.f64 %7, t, 0d3FE0000000000000, %7;\n"
+        "}"
+        : "+d"(hi0), "+d"(hi1), "+d"(lw0), "+d"(lw1), "+d"(p0), "+d"(p1), "+d"(m0), "+d"(m1)
+        : "r"(z0), "r"(meta), "d"(x.x), "d"(x.y), "d"(y.x), "d"(y.y), "d"(h.x), "d"(h.y));
+}
+
 // store two consecutive levels, or only the first when the column ends between them (one
 // predicated pair instead of two divergent code paths)
 __device__ __forceinline__ void wt_store2(double *p, double a, double b, bool both)
@@ -519,7 +572,7 @@ __device__ __forceinline__ void wt_next(const Arrays &A, const WtView &V, int la
 // VLIMIT_ONE: the vertical 3-point stencil over the cluster bounds (vlimit == 1, reference.cpp:380-392);
 // else A.vlimit is 2 or 3 (docs/refactoring.md:113-148): the cluster bound of a level is widened (2) or
 // narrowed (3) by the node's own a1 maxima of levels z-1 .. z+1, which stand in the staged own row
-template <bool VLIMIT_ONE>
+template <bool VLIMIT_ONE, bool FOLD = false>
 __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int wi, int lane, size_t tn,
                                           const double *g_lo, const double *g_v, const WtEarly &E, int raw, int &wn,
                                           WtEarly &En)
@@ -530,10 +583,12 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
     {
         // own column: needed after the gather only
         if (I.out) {
-            const double2 ll = __ldg(reinterpret_cast<const double2 *>(g_lo + I.grow));
             const double2 aa = __ldg(reinterpret_cast<const double2 *>(A.area_inv + I.grow));
-            l0 = ll.x; l1 = ll.y;
             ai0 = aa.x; ai1 = aa.y;
+            if (!FOLD) {   // (folded: the staged own row still holds the raw fct_LO, see below)
+                const double2 ll = __ldg(reinterpret_cast<const double2 *>(g_lo + I.grow));
+                l0 = ll.x; l1 = ll.y;
+            }
         }
         // cluster bounds start from the (-big, +big) fill of ring elements that already ended
         // (reference.cpp:341-349) and the node's own a1 bounds
@@ -544,13 +599,17 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
         lw1 = fl1 ? A.big : CUDART_INF;
         const double2 x = *reinterpret_cast<const double2 *>(I.ra + I.own);
         const double2 y = *reinterpret_cast<const double2 *>(I.rb + I.own);
+        if (FOLD) {
+            l0 = x.x;
+            l1 = x.y;
+        }
         if (I.act && z0 < I.sd) {
-            hi0 = pick_max(hi0, x.x);
-            lw0 = pick_min(lw0, y.x);
+            hi0 = pick_max(hi0, FOLD ? pick_max(x.x, y.x) : x.x);
+            lw0 = pick_min(lw0, FOLD ? pick_min(x.x, y.x) : y.x);
         }
         if (I.act && z0 + 1 < I.sd) {
-            hi1 = pick_max(hi1, x.y);
-            lw1 = pick_min(lw1, y.y);
+            hi1 = pick_max(hi1, FOLD ? pick_max(x.y, y.y) : x.y);
+            lw1 = pick_min(lw1, FOLD ? pick_min(x.y, y.y) : y.y);
         }
         wt_b1v(E.f0, E.f1, E.f2, p0, p1, m0, m1);
     }
@@ -562,7 +621,8 @@ __device__ __forceinline__ void wt_item_a(const Arrays &A, const WtView &V, int 
         const double2 x = *reinterpret_cast<const double2 *>(I.ra + e.y);
         const double2 y = *reinterpret_cast<const double2 *>(I.rb + e.y);
         const double2 h = *reinterpret_cast<const double2 *>(I.re + e.x);
-        wt_edge_a(z0, e.z, x, y, h, hi0, hi1, lw0, lw1, p0, p1, m0, m1);
+        if (FOLD) wt_edge_a_fold(z0, e.z, x, y, h, hi0, hi1, lw0, lw1, p0, p1, m0, m1);
+        else wt_edge_a(z0, e.z, x, y, h, hi0, hi1, lw0, lw1, p0, p1, m0, m1);
     }
     // ---- vertical 3-point stencil of a3 (reference.cpp:380-392): neighbouring slots are the
     // neighbouring lanes (ghost slots included) ----
@@ -853,17 +913,19 @@ __device__ __forceinline__ void reg_alloc()
 // full issue priority, instead of two converter warps taking 2.2 us of every 4 us refill (WT_TRACE).
 constexpr int WT_CONV_CHUNKS = 16;
 template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false, int RC = 0, int NCV = WT_CONVERTERS>
-__global__ void __launch_bounds__((RC > 0 ? wt_producer_warps(RC) : NPW + 1 + (PHASE_A ? NCV : 0)) * 32 + NWC * 32, 1)
+__global__ void __launch_bounds__((RC > 0 ? wt_producer_warps(RC) : NPW + 1 + ((PHASE_A && NCV > 0) ? NCV : 0)) * 32 + NWC * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
 {
     extern __shared__ __align__(128) unsigned char wt_sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // first consumer warp
-    constexpr int NPROD = RC > 0 ? wt_producer_warps(RC) : NPW + 1 + (PHASE_A ? NCV : 0);
+    constexpr int NPROD = RC > 0 ? wt_producer_warps(RC) : NPW + 1 + ((PHASE_A && NCV > 0) ? NCV : 0);
     constexpr int PREGS = wt_producer_regs(RC);
+    constexpr bool FOLD = PHASE_A && NCV < 0;     // no a1 pass: the consumers read the raw (fct_LO, ttf) rows
+    static_assert(!FOLD || VLIMIT_ONE, "the vlimit variants read the own a1 maxima from the converted row");
     constexpr bool CONSUMERS_CONVERT = PHASE_A && NCV == 0;
     constexpr int NCH = CONSUMERS_CONVERT ? WT_CONV_CHUNKS : 0;   // conversion chunks ahead of a tile's warp items
-    static_assert(RC == 0 || (NPW + 1 + (PHASE_A ? NCV : 0) <= NPROD && NWC % 4 == 0 &&
+    static_assert(RC == 0 || (NPW + 1 + ((PHASE_A && NCV > 0) ? NCV : 0) <= NPROD && NWC % 4 == 0 &&
                               NPROD * 32 * PREGS + NWC * 32 * RC <= (NPROD + NWC) * 32 * ((65536 / ((NPROD + NWC) * 32)) & ~7) &&
                               RC % 8 == 0),
                   "register budget of the re-allocated roles");
@@ -1058,7 +1120,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             if (tile_of[s] < 0) break;
             const int tr = tracer_of[s];
             const bool first_loads_ahead = T.opt & 2;
-            if (!first_loads_ahead && !CONSUMERS_CONVERT) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            if (!first_loads_ahead && !CONSUMERS_CONVERT) mbar_wait((PHASE_A && !FOLD) ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             const WtView V = wt_view(wt_sm + WT_SMEM_HEAD + (size_t)s * stage_bytes);
             const size_t tn = tr * A.ts_node;
             const double *g_v = A.adf_v + tr * A.ts_nodev;
@@ -1090,14 +1152,14 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
             }
             WtEarly E;
             if (wi < V.n_witems) E = wt_early<PHASE_A, ITER>(A, V, wi, lane, g_v, tn);
-            if (first_loads_ahead || CONSUMERS_CONVERT) mbar_wait(PHASE_A ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
+            if (first_loads_ahead || CONSUMERS_CONVERT) mbar_wait((PHASE_A && !FOLD) ? b_ready(s) : b_rows(s), (it / NSTAGE) & 1);
             if (warp == NPROD) wt_trace(T, it, 6);
             if (warp == NPROD + NWC - 1) wt_trace(T, it, 8);
             while (wi < V.n_witems) {
                 WtEarly En;
                 int wn = 0;
                 const int raw = draw(s);
-                if (PHASE_A) wt_item_a<VLIMIT_ONE>(A, V, wi, lane, tn, A.lo + tn, g_v, E, raw, wn, En);
+                if (PHASE_A) wt_item_a<VLIMIT_ONE, FOLD>(A, V, wi, lane, tn, A.lo + tn, g_v, E, raw, wn, En);
                 else if (ITER)
                     wt_item_b_iter(A, V, wi, lane, tn, g_v, A.adf_v2 + tr * A.ts_nodev, A.adf_h2 + tr * A.ts_edge, E, raw, wn, En);
                 else

@@ -162,7 +162,12 @@ void free_stream_(void **stream, int *istat);
 void fct_ale_set_fused_(int *fused);
 /* tuning knob: same effect as the environment variable FCT_<name> (NUL-terminated name), e.g.
  * "TILE" 0/1, "TILE_NODES", "TILE_ITERS" (read when a plan is created), "TILE_VARIANT_A",
- * "TILE_VARIANT_B", "TILE_AHEAD" (read at every launch).  Results never depend on them. */
+ * "TILE_VARIANT_B", "TILE_AHEAD" (read at every launch).  Warp-item kernels: "WT_STAGES", "WT_NODES",
+ * "WT_SMEM" (plan), "WT_OPT" (bit mask of scheduling options), "WT_ISSUERS", "WT_WARPS_A", "WT_WARPS_B",
+ * "WT_CONV" (phase A: -1 a1 folded into the edge loop = default, 2 / 3 / 4 converter warps, 0 consumers run
+ * the a1 pass), "WT_REGS" (0 | 72 | 80 | 88: register re-allocation between the warp roles, setmaxnreg),
+ * "WT_TRACE", "HALO_SKIP", "DIRECT_COPY" (launch).  Results never depend on them (measured alternatives,
+ * DESIGN.md 3.3 / 3.4) -- except the timing experiments "WT_DIAG" and "HALO_SKIP", which skip data movement. */
 void fct_ale_tune_(const char *name, int *value);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 void fct_ale_launch_count_(long long *count);
