@@ -314,7 +314,10 @@ def gpu_reference(m, abi, reps=3):
     if not os.path.exists(REF_GPU_SO):
         return {"unavailable": "baseline/_ref/libref_gpu_kernels.so not built (needs /root/reference at build time)"}
     import ctypes as C
-    lib = C.CDLL(REF_GPU_SO)
+    try:
+        lib = C.CDLL(REF_GPU_SO)
+    except OSError as exc:
+        return {"unavailable": f"baseline/_ref/libref_gpu_kernels.so does not load: {exc}"}
     ms = (C.c_double * 12)()
     st = C.c_int()
     ci, ip = abi.ci, abi.iptr

@@ -401,17 +401,22 @@ __device__ __forceinline__ void wt_b1v(double f0, double f1, double f2, double &
 }
 
 // One edge of phase B for two levels (docs/refactoring.md:246-261 + :303-314).  n1 = edges[2g],
-// n2 = edges[2g+1]; h >= 0: ae = min(1, plus[n1], minus[n2]) else min(1, minus[n1], plus[n2]) in
-// that order; the own node is n2 when `second`.  hl = ae*h (identical on both end nodes);
-// dh +-= hl * (dt/area).
+// n2 = edges[2g+1]; h >= 0: ae = min(1, plus[n1], minus[n2]) else min(1, minus[n1], plus[n2]); the own node is
+// n2 when `second`.  hl = ae*h (identical on both end nodes); dh +-= hl * (dt/area).
+// Written so that the own node's share is hoisted out of the edge loop: with p1 = min(1, plus[own]) and
+// m1 = min(1, minus[own]) (per level, computed once per item), u = min(p1, minus[other]) and
+// v = min(m1, plus[other]) are the two candidates whatever the roles -- first end: h >= 0 ? u : v; second end:
+// h >= 0 ? min(1, plus[other], minus[own]) = v : u -- so ae = ((h >= 0) xor second) ? u : v: three compares and
+// three selects per level instead of three and six (min is exact and associative: the same value as the
+// listing's min(1, a, b) in any order).
 __device__ __forceinline__ void wt_edge_b(int z0, int meta, const double2 &po, const double2 &mo, const double2 &h,
-                                          double pn0, double pn1, double mn0, double mn1, double ar0, double ar1,
+                                          double p10, double p11, double m10, double m11, double ar0, double ar1,
                                           double &dh0, double &dh1, double &hl0, double &hl1)
 {
     asm("{\n"
         ".reg .pred P0, P1, S, q, r;\n"
         ".reg .b32 dg, sg, a, b, z1;\n"
-        ".reg .f64 own, oth, x1, x2, ae, t;\n"
+        ".reg .f64 u, v, ae, t;\n"
         "and.b32 dg, %5, 0xffff;\n"
         "and.b32 sg, %5, 0x80000000;\n"
         "add.s32 z1, %4, 1;\n"
@@ -419,15 +424,12 @@ __device__ __forceinline__ void wt_edge_b(int z0, int meta, const double2 &po, c
         "setp.lt.s32 P1, z1, dg;\n"
         "setp.lt.s32 S, %5, 0;\n"
         // level z0
+        "setp.lt.f64 r, %8, %12;\n"
+        "selp.f64 u, %8, %12, r;\n"
+        "setp.lt.f64 r, %6, %14;\n"
+        "selp.f64 v, %6, %14, r;\n"
         "setp.ge.xor.f64 q, %10, 0d0000000000000000, S;\n"
-        "selp.f64 own, %12, %14, q;\n"
-        "selp.f64 oth, %8, %6, q;\n"
-        "selp.f64 x1, oth, own, S;\n"
-        "selp.f64 x2, own, oth, S;\n"
-        "setp.lt.f64 r, x1, 0d3FF0000000000000;\n"
-        "selp.f64 ae, x1, 0d3FF0000000000000, r;\n"
-        "setp.lt.f64 r, x2, ae;\n"
-        "selp.f64 ae, x2, ae, r;\n"
+        "selp.f64 ae, u, v, q;\n"
         "mul.rn.f64 %2, ae, %10;\n"
         "mov.b64 {a, b}, %2;\n"
         "xor.b32 b, b, sg;\n"
@@ -435,15 +437,12 @@ __device__ __forceinline__ void wt_edge_b(int z0, int meta, const double2 &po, c
         "mul.rn.f64 t, t, %16;\n"
         "@P0 add.rn.f64 %0, %0, t;\n"
         // level z0+1
+        "setp.lt.f64 r, %9, %13;\n"
+        "selp.f64 u, %9, %13, r;\n"
+        "setp.lt.f64 r, %7, %15;\n"
+        "selp.f64 v, %7, %15, r;\n"
         "setp.ge.xor.f64 q, %11, 0d0000000000000000, S;\n"
-        "selp.f64 own, %13, %15, q;\n"
-        "selp.f64 oth, %9, %7, q;\n"
-        "selp.f64 x1, oth, own, S;\n"
-        "selp.f64 x2, own, oth, S;\n"
-        "setp.lt.f64 r, x1, 0d3FF0000000000000;\n"
-        "selp.f64 ae, x1, 0d3FF0000000000000, r;\n"
-        "setp.lt.f64 r, x2, ae;\n"
-        "selp.f64 ae, x2, ae, r;\n"
+        "selp.f64 ae, u, v, q;\n"
         "mul.rn.f64 %3, ae, %11;\n"
         "mov.b64 {a, b}, %3;\n"
         "xor.b32 b, b, sg;\n"
@@ -452,8 +451,8 @@ __device__ __forceinline__ void wt_edge_b(int z0, int meta, const double2 &po, c
         "@P1 add.rn.f64 %1, %1, t;\n"
         "}"
         : "+d"(dh0), "+d"(dh1), "=&d"(hl0), "=&d"(hl1)
-        : "r"(z0), "r"(meta), "d"(po.x), "d"(po.y), "d"(mo.x), "d"(mo.y), "d"(h.x), "d"(h.y), "d"(pn0), "d"(pn1),
-          "d"(mn0), "d"(mn1), "d"(ar0), "d"(ar1));
+        : "r"(z0), "r"(meta), "d"(po.x), "d"(po.y), "d"(mo.x), "d"(mo.y), "d"(h.x), "d"(h.y), "d"(p10), "d"(p11),
+          "d"(m10), "d"(m11), "d"(ar0), "d"(ar1));
 }
 
 struct WtView {
@@ -736,6 +735,8 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
     }
     const double ar0 = A.dt / E.a0, ar1 = A.dt / E.a1;
     double dh0 = q_dh.x, dh1 = q_dh.y;
+    // the own node's share of every edge factor, once per item (see wt_edge_b)
+    const double p10 = pick_min(1., pp.x), p11 = pick_min(1., pp.y), m10 = pick_min(1., mm.x), m11 = pick_min(1., mm.y);
     // ---- b3 horizontal + c horizontal over the node's edges, ascending edge id ----
 #pragma unroll 2
     for (int k = 0; k < I.cnt; ++k) {
@@ -744,7 +745,7 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
         const double2 mo = *reinterpret_cast<const double2 *>(I.rb + e.y);
         const double2 h = *reinterpret_cast<const double2 *>(I.re + e.x);
         double hl0, hl1;
-        wt_edge_b(z0, e.z, po, mo, h, pp.x, pp.y, mm.x, mm.y, ar0, ar1, dh0, dh1, hl0, hl1);
+        wt_edge_b(z0, e.z, po, mo, h, p10, p11, m10, m11, ar0, ar1, dh0, dh1, hl0, hl1);
         const int dg = e.z & 0xffff;
         if ((e.z & 0x40000000) && z0 < dg) wt_store2(g_ho + (unsigned)e.w + z0, hl0, hl1, z0 + 1 < dg);
     }
