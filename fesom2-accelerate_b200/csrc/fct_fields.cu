@@ -93,6 +93,7 @@ static Arrays arrays_of(const Fields *f, int mode, double dt, double eps, double
     A.dt = dt;
     A.eps = eps;
     A.big = big;
+    A.flags = tune_int("FCT_WT_FLAGS", 0);
     return A;
 }
 

@@ -259,6 +259,20 @@ __device__ __forceinline__ double limit_quotient(double a, double b)
 }
 
 
+// min(1, x) as one compare + one select (the C++ form compiles to DSETP.MIN + FSEL + SEL + LOP3)
+__device__ __forceinline__ double min_one(double x)
+{
+    double o;
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.lt.f64 p, %1, 0d3FF0000000000000;\n"
+        "selp.f64 %0, %1, 0d3FF0000000000000, p;\n"
+        "}"
+        : "=d"(o)
+        : "d"(x));
+    return o;
+}
+
 // ---- hot inner bodies in PTX: ptxas keeps the predicated form (one DSETP...AND + two FSEL per
 // bound update, one DSETP + one predicated DADD per sum) where the C++ form was if-converted into
 // branches and select chains (2.5x the instructions) ---------------------------------------------
@@ -537,13 +551,18 @@ __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, in
         if (z0 + 2 <= nz) E.f2 = __ldg(g_v + grow + 2);
         E.f0 = ff.x;
         E.f1 = ff.y;
+        if (PHASE_A) {
+            // area_inv is loaded at the top of its item and first used after the edge loop, a few hundred cycles
+            // later: less than a DRAM access.  Pull it into L2 one item ahead (one probe per 64 bytes)
+            if ((z0 & 7) == 0 && (A.flags & 2)) prefetch_l2(A.area_inv + grow);
+        }
         if (!PHASE_A) {
             const double2 aa = __ldg(reinterpret_cast<const double2 *>(A.area + grow));
             E.a0 = aa.x;
             E.a1 = aa.y;
             // the operands of c vertical are consumed after the item's edge loop: pull them into L2
             // now (one probe per 64 bytes) instead of holding 24 registers for loads in flight
-            if (!ITER && (z0 & 7) == 0) {
+            if (!ITER && (z0 & 7) == 0 && !(A.flags & 1)) {
                 prefetch_l2(A.del_v + tn + grow);
                 prefetch_l2(A.del_h + tn + grow);
                 prefetch_l2(A.ttf + tn + grow);
@@ -693,50 +712,26 @@ __device__ __forceinline__ void wt_item_b(const Arrays &A, const WtView &V, int 
     const double p_p2 = *reinterpret_cast<const double *>(pr + 16);
     const double m_p2 = *reinterpret_cast<const double *>(mr + 16);
     // ---- b3 vertical, docs/refactoring.md:205-231 (the bottom flux stays) ----
+    // Interface z between levels z-1 and z: flux >= 0: ae = min(1, minus[z-1], plus[z]); else min(1, plus[z-1],
+    // minus[z]); the surface (z = 0) sees only its own level.  Branch-free: both candidates from the hoisted
+    // p1 = min(1, plus), m1 = min(1, minus) of the two own levels, then one select on the sign (a warp holds both
+    // signs, so the branchy form ran both sides anyway); ae = 1 leaves a flux untouched exactly.
+    const double p10 = min_one(pp.x), p11 = min_one(pp.y), m10 = min_one(mm.x), m11 = min_one(mm.y);
     double fl0, fl1, fl2;
     {
-        double ae = 1.;
-        if (z0 == 0) {
-            ae = pick_min(ae, (E.f0 >= 0.) ? pp.x : mm.x);
-        } else if (E.f0 >= 0.) {
-            ae = pick_min(ae, m_m1);
-            ae = pick_min(ae, pp.x);
-        } else {
-            ae = pick_min(ae, p_m1);
-            ae = pick_min(ae, mm.x);
-        }
-        fl0 = ae * E.f0;
+        const bool top = z0 == 0;
+        const double up_m = top ? 1. : m_m1, up_p = top ? 1. : p_m1;       // level z0-1 (none above the surface)
+        const double ae0 = (E.f0 >= 0.) ? pick_min(p10, up_m) : pick_min(m10, up_p);
+        const double ae1 = (E.f1 >= 0.) ? pick_min(p11, mm.x) : pick_min(m11, pp.x);
+        const double ae2 = (E.f2 >= 0.) ? pick_min(min_one(p_p2), mm.y) : pick_min(min_one(m_p2), pp.y);
+        fl0 = ae0 * E.f0;
+        fl1 = ((z0 + 1 < nz) ? ae1 : 1.) * E.f1;
+        fl2 = ((z0 + 2 < nz) ? ae2 : 1.) * E.f2;
     }
-    if (z0 + 1 < nz) {
-        double ae = 1.;
-        if (E.f1 >= 0.) {
-            ae = pick_min(ae, mm.x);
-            ae = pick_min(ae, pp.y);
-        } else {
-            ae = pick_min(ae, pp.x);
-            ae = pick_min(ae, mm.y);
-        }
-        fl1 = ae * E.f1;
-    } else {
-        fl1 = E.f1;
-    }
-    if (z0 + 2 < nz) {
-        double ae = 1.;
-        if (E.f2 >= 0.) {
-            ae = pick_min(ae, mm.y);
-            ae = pick_min(ae, p_p2);
-        } else {
-            ae = pick_min(ae, pp.y);
-            ae = pick_min(ae, m_p2);
-        }
-        fl2 = ae * E.f2;
-    } else {
-        fl2 = E.f2;
-    }
+    // (a cached dt / area array instead of these two divisions was measured neutral: profiles/r2_v15_*)
     const double ar0 = A.dt / E.a0, ar1 = A.dt / E.a1;
     double dh0 = q_dh.x, dh1 = q_dh.y;
-    // the own node's share of every edge factor, once per item (see wt_edge_b)
-    const double p10 = pick_min(1., pp.x), p11 = pick_min(1., pp.y), m10 = pick_min(1., mm.x), m11 = pick_min(1., mm.y);
+    // (p10 .. m11: the own node's share of every edge factor, see wt_edge_b)
     // ---- b3 horizontal + c horizontal over the node's edges, ascending edge id ----
 #pragma unroll 2
     for (int k = 0; k < I.cnt; ++k) {

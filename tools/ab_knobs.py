@@ -14,7 +14,7 @@ nx, ny, nl = [int(x) for x in sys.argv[1].split("x")]
 cfgs = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in c.split(",") if kv) for c in sys.argv[2].split(";")]
 rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 allk = sorted({k for c in cfgs for k in c})
-DEFAULTS = {"WT_REGS": 0, "WT_OPT": -1, "WT_ISSUERS": 0, "WT_WARPS_A": 0, "WT_WARPS_B": 0, "WT_CONV": -1}
+DEFAULTS = {"WT_REGS": 0, "WT_OPT": -1, "WT_ISSUERS": 0, "WT_WARPS_A": 0, "WT_WARPS_B": 0, "WT_CONV": -1, "WT_FLAGS": 0}
 m = mesh.make_mesh(nx, ny, nl)
 f = mesh.fast_fields(m) if m.myDim_nod2D > 500000 else mesh.make_fields(m, with_uv=False, poison=False)
 Sn, Sg = m.S_n(), m.S_g()
