@@ -238,7 +238,10 @@ def run_reference(args):
     same = avail is None or need < 0.8 * avail
     if same:
         ctx = mp.get_context("fork")
-        port = 20000 + (os.getpid() % 20000)
+        import socket
+        with socket.socket() as sk:             # a free port for the workers' own gloo rendezvous
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
         pipes, procs = [], []
         for r in range(cores):
             a, b = ctx.Pipe(duplex=False)

@@ -39,6 +39,10 @@ def main():
     assert np.array_equal(lf.fct_adf_h, want.fct_adf_h[part.mesh.edge_gid])
     # max-over-ranks reduction used for timings
     assert comm.max_over_ranks(float(rank)) == float(world - 1)
+    # digests: one Python integer per rank, summed modulo 2^64
+    assert comm.sum_mod64((1 << 63) + 5 + rank) == (world * ((1 << 63) + 5) + world * (world - 1) // 2) % (1 << 64)
+    tot = comm.sum_mod64(mesh_mod.digest_node_array(part.mesh, lf.fct_plus, 0))
+    assert tot == mesh_mod.digest_node_array(m, want.fct_plus, 0)
     dist.barrier()
     open(os.path.join(out, f"ok_{rank}"), "w").close()
     dist.destroy_process_group()

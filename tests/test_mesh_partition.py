@@ -216,3 +216,52 @@ def test_graph_grown_partition_of_an_unstructured_mesh_equals_single_domain(mesh
         for k in ("fct_ttf_max", "fct_ttf_min", "fct_plus", "fct_minus", "fct_adf_v", "del_ttf_advvert", "del_ttf_advhoriz"):
             assert np.array_equal(getattr(lf, k)[:n], getattr(want, k)[g]), k
         assert np.array_equal(lf.fct_adf_h, want.fct_adf_h[p.mesh.edge_gid])
+
+
+def test_fast_fields_and_digest_are_functions_of_global_ids(mesh_mod):
+    """bench.py's determinism claim rests on two properties checked here on the CPU: the synthetic
+    fields of a partition are exactly the rows of the single-domain fields (every cell a function of
+    its global row id, level and array), and the per-partition digests of a node array add up (mod
+    2^64) to the single-domain digest -- for contiguous and for graph-grown partitions -- while a
+    one-ulp change of one owned cell changes it."""
+    m = mesh_mod.make_mesh(90, 70, 25, seed=2)
+    f = mesh_mod.fast_fields(m, seed=1)
+    want = mesh_mod.digest_node_array(m, f.ttf, 3)
+    for owner in (None, mesh_mod.grow_partition(m, 4, seed=1)):
+        tot = 0
+        for p in mesh_mod.partition_mesh(m, 4, owner=owner):
+            lf = mesh_mod.fast_fields(p.mesh, seed=1)
+            sf = mesh_mod.slice_fields(f, p)
+            for k in ("ttf", "fct_LO", "fct_adf_v", "fct_adf_h", "area", "area_inv", "hnode", "hnode_new",
+                      "del_ttf_advvert", "del_ttf_advhoriz"):
+                assert np.array_equal(getattr(lf, k), getattr(sf, k)), k
+            tot = (tot + mesh_mod.digest_node_array(p.mesh, lf.ttf, 3)) & (2 ** 64 - 1)
+        assert tot == want
+    g = f.ttf.copy()
+    g[7, 2] = np.nextafter(g[7, 2], np.inf)
+    assert mesh_mod.digest_node_array(m, g, 3) != want
+    assert mesh_mod.digest_node_array(m, f.ttf, 4) != want           # the salt separates the arrays
+    # inactive levels are not part of the digest
+    dead = np.arange(m.L)[None, :] >= (m.nlevels_nod2D[:, None] - 1)
+    h = f.ttf.copy()
+    h[dead] = -123.0
+    assert mesh_mod.digest_node_array(m, h, 3) == want
+
+
+def test_reference_arm_of_bench_runs_the_same_mesh_and_its_digest_is_partition_independent():
+    """`bench.py --impl reference` on the pi mesh: the CPU arm splits the workload mesh over the host
+    cores (forked processes, host exchange_nod over gloo); whatever the number of partitions, the
+    digests of its outputs are those of the single process."""
+    import json
+    outs = []
+    for cores in ("0", "0-2"):
+        r = subprocess.run(["taskset", "-c", cores, sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                            "--workload", "pi", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["details"]["same_mesh_as_product_arm"] is True
+        assert line["config"]["workload"] == "pi" and line["e2e"]["value"] == line["value"]
+        outs.append(line)
+    assert outs[0]["cpu_baseline"]["cores"] == 1 and outs[1]["cpu_baseline"]["cores"] == 3
+    assert outs[0]["digest"] == outs[1]["digest"] and len(outs[0]["digest"]) == 4
+    assert outs[0]["config"] == outs[1]["config"]
