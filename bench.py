@@ -94,7 +94,13 @@ class ClockSampler:
             return None
         time.sleep(0.15)
         self.p.terminate()
-        sel = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
+        # samples inside the timed region; a region shorter than the 100 ms sampling interval may hold none: then
+        # the samples nearest to it (the pre-roll right before it runs the same steps at the same load)
+        sel = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15]
+        inside = len(sel)
+        if not sel:
+            near = sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:3]
+            sel = [r for ts, r in near if min(abs(ts - t0), abs(ts - t1)) <= 1.0]
         if not sel:
             return None
         sm = sorted(float(r[0]) for r in sel if r[0].replace(".", "").isdigit())
@@ -103,7 +109,7 @@ class ClockSampler:
             if any(len(r) > col and r[col].lower().startswith("active") for r in sel):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(sel[0][1]) if sel[0][1] else None,
-                "reasons": reasons, "samples": len(sel)}
+                "reasons": reasons, "samples": len(sel), "samples_inside_timed_region": inside}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -475,6 +481,9 @@ def run_product(args):
         df.stream.sync()
         return ms_
 
+    # (started before the warm-up: nvidia-smi needs a moment before its first sample, and at N = 8 the timed region
+    #  of 20 steps is shorter than its 100 ms sampling interval)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     est = 0.0
     if args.warmup > 0:
         est = hostcomm.max_over_ranks(timed_steps(args.warmup)) / args.warmup
@@ -483,7 +492,6 @@ def run_product(args):
     n_pre = int(min(5000, max(0, np.ceil(args.preroll * 1e3 / est)))) if (est > 0 and args.preroll > 0) else 0
     preroll_s = hostcomm.max_over_ranks(timed_steps(n_pre)) * 1e-3 if n_pre else 0.0
     hostcomm.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     n0 = abi.launch_count()
     t0 = time.time()
     ms = timed_steps(args.steps)
