@@ -507,16 +507,22 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     const bool vl = isA && A.vlimit != 1 && A.vlimit != 0;
     const WarpVariant *table = vl ? g_wvariants_vl : (iter ? g_wvariants_it : g_wvariants);
     int vi = -1, best = 1 << 30;
-    for (int i = 0; i < (vl ? NVL : (iter ? NVI : NV1)); ++i) {
-        if (table[i].stages != stages || table[i].phase_a != isA || table[i].regs != regs) continue;
-        if (isA && plain && table[i].conv != conv) continue;
-        const int dist = 4 * std::abs(table[i].consumers - nwc) + std::abs(table[i].issuers - npw);
-        if (dist < best) {
-            best = dist;
-            vi = i;
+    // the closest compiled shape; a knob combination nobody compiled (e.g. three converter warps without the
+    // 32-warp CTA) falls back to the same ring depth and register scheme with any a1 scheme
+    for (int pass = 0; pass < 2 && vi < 0; ++pass)
+        for (int i = 0; i < (vl ? NVL : (iter ? NVI : NV1)); ++i) {
+            if (table[i].stages != stages || table[i].phase_a != isA || table[i].regs != regs) continue;
+            if (pass == 0 && isA && plain && table[i].conv != conv) continue;
+            const int dist = 4 * std::abs(table[i].consumers - nwc) + std::abs(table[i].issuers - npw);
+            if (dist < best) {
+                best = dist;
+                vi = i;
+            }
         }
+    if (vi < 0) {
+        std::fprintf(stderr, "fesom2-accelerate: no warp-item kernel compiled for %d stages with WT_REGS %d\n", stages, regs);
+        return false;
     }
-    if (vi < 0) return false;
     const WarpVariant &v = table[vi];
     const size_t smem = WT_SMEM_HEAD + (size_t)stages * stage_bytes;
     bool first = false;

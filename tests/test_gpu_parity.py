@@ -110,6 +110,34 @@ def test_warp_item_kernel_variants(mesh_mod, harness, abi, oracle_mod, name, kno
             abi.tune(k, v)
 
 
+@pytest.mark.parametrize("name", ["pi", "deep"])
+@pytest.mark.parametrize("knobs", [dict(WT_CONV=2), dict(WT_CONV=3), dict(WT_CONV=4), dict(WT_CONV=0), dict(WT_CONV=-1, WT_ISSUERS=2),
+                                   dict(WT_REGS=80), dict(WT_REGS=88), dict(WT_REGS=72), dict(WT_REGS=72, WT_CONV=3),
+                                   dict(WT_CONV=-1, WT_WARPS_A=24, WT_WARPS_B=24, WT_ISSUERS=3),
+                                   dict(WT_OPT=14), dict(WT_OPT=22), dict(WT_OPT=38), dict(WT_OPT=70), dict(WT_FLAGS=3)])
+def test_round2_kernel_alternatives_are_bit_identical(mesh_mod, harness, abi, oracle_mod, name, knobs):
+    """Every measured alternative of DESIGN.md 3.4 (who runs the a1 pass, setmaxnreg register re-allocation
+    between the warp roles, the 32-warp CTA, how the producers wait, the prefetch switches) on the packed
+    storage, nl = 48 (three-stage ring) and nl = 80 (two stages, copy lists ahead): the same bits as the oracle."""
+    m, f = cases(mesh_mod, name)
+    want = f.copy()
+    oracle_mod.fct_ale(m, want)
+    defaults = dict(WT_CONV=-1, WT_REGS=0, WT_OPT=-1, WT_FLAGS=0, WT_WARPS_A=0, WT_WARPS_B=0, WT_ISSUERS=0)
+    plan = harness.DevicePlan(m)
+    df = harness.DeviceFields(plan, 1, packed=True)
+    try:
+        for k, v in knobs.items():
+            abi.tune(k, v)
+        df.upload(f)
+        assert df.step(f, mode=1) == 10
+        check(df.download(f, mode=1), want)
+    finally:
+        for k, v in defaults.items():
+            abi.tune(k, v)
+        df.free()
+        plan.free()
+
+
 @pytest.mark.parametrize("name", ["tiny", "pi", "core2", "deep", "delaunay"])
 def test_packed_level_storage(mesh_mod, harness, oracle_mod, name):
     """The fast path's own layout: columns hold their active levels only, back to back."""
