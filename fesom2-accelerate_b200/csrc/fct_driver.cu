@@ -338,7 +338,8 @@ static void build_plan_wtiles(Plan *p, const DerivedHost &d, const int *nlev_n)
         T.ntiles = h[s].ntiles;
         T.smem_bytes = h[s].smem_bytes;
         T.max_copies = 0;
-        for (int t = 0; t < h[s].ntiles; ++t) T.max_copies = std::max(T.max_copies, (int)h[s].blob[h[s].blob_off[t]].x);
+        for (int t = 0; t < h[s].ntiles; ++t)   // copies + L2 prefetch entries: what must fit the slot that travels ahead
+            T.max_copies = std::max(T.max_copies, (int)h[s].blob[h[s].blob_off[t]].x + (int)h[s].blob[h[s].blob_off[t] + 3].x);
         if (!T.blob || !T.blob_off) return;
         if (verbose && h[s].ntiles > 0)
             std::fprintf(stderr,
@@ -468,7 +469,10 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // measured (profiles/r1_v11_sched_options_sweep_mid.log, r1_v14_ab_ring_depth.log): first loads before
     // the rows wait (2) is +10 % on phase A; lists ahead (4) pays with a two-stage ring only; suspended
     // producers (1) are neutral
-    if (T.opt < 0) T.opt = 2 | (stages == 2 ? 4 : 0);
+    // round 2 (profiles/r2_v21_*): the issuers pull the own columns of the arrays the consumers load from global memory
+    // into L2 tile by tile (128): phase A +1..3 %, phase B +3 % with three stages, -1 % with two (there the per-item
+    // probes of the consumers stay)
+    if (T.opt < 0) T.opt = 2 | (stages == 2 ? 4 : 0) | ((isA || stages != 2) ? 128 : 0);
     if (T.max_copies > WT_PRE_MAX_COPIES || T.diag != 0) T.opt &= ~4;
     if (WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) {
         std::fprintf(stderr, "fesom2-accelerate: warp tiles of %d B do not fit two stages\n", stage_bytes);
@@ -568,8 +572,10 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
         T.trace = g_trace;
     }
     dim3 grid((unsigned)std::min<long long>(total, sms), 1, 1);
+    Arrays Aw = A;
+    if (T.opt & 128) Aw.flags |= 4;   // tile-level L2 prefetch by the issuers: the consumers skip their per-item probes
     const int warps = v.regs > 0 ? wt_producer_warps(v.regs) + v.consumers : v.issuers + 1 + (isA ? std::max(v.conv, 0) : 0) + v.consumers;
-    v.fn<<<grid, warps * 32, smem, s>>>(A, T, ntracers, stage_bytes, ctr);
+    v.fn<<<grid, warps * 32, smem, s>>>(Aw, T, ntracers, stage_bytes, ctr);
     count_launch(1);
     return cuda_ok(cudaGetLastError(), "warp kernel launch");
 }

@@ -29,7 +29,9 @@ struct Arrays {
     size_t ts_node, ts_nodev, ts_edge, ts_uv;   // tracer strides (doubles; double2 for uv)
     // mesh-static arrays (shared by all tracers)
     const double *area, *area_inv, *hnode, *hnode_new;
-    int flags;   // timing experiments of the warp-item kernels (results unaffected): 1 = no L2 prefetch of the c-vertical operands
+    int flags;   // warp-item kernels (results unaffected): 1 = no per-item L2 prefetch of the c-vertical operands (timing
+                 // experiment), 2 = area_inv probed one item ahead in phase A, 4 = set by the launcher when the issuers
+                 // prefetch whole tiles (WT_OPT 128): the consumers skip their per-item probes
     int pitchL;   // row pitch of [node][nl-1] arrays
     int pitchV;   // row pitch of [node][nl] arrays (fct_adf_v, area, area_inv)
     int pitchH;   // row pitch of fct_adf_h

@@ -301,7 +301,7 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
     std::vector<Copy> copies;
 
     auto need_bytes = [&](size_t nrows, size_t nerows, size_t nn, size_t nent, size_t nsched, int rb, int eb) {
-        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows) * 8) + nn * 16 + nent * 16 +
+        const size_t blob = WT_HDR_BYTES + pad16((int)(2 * nrows + nerows + WT_MAX_PREFETCH) * 8) + nn * 16 + nent * 16 +
                             pad16((int)((nsched + W - 1) / W * W) * 2);
         return 16 + blob + 2 * (size_t)rb + (size_t)eb + slack + 256;   // + the schedule's re-ordering margin
     };
@@ -476,7 +476,21 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         std::stable_sort(copies.begin(), copies.end(), [](const Copy &x, const Copy &y) { return x.bytes > y.bytes; });
         const int off_rows = WT_HDR_BYTES;
         const int n_copies = (int)copies.size();
-        const int off_hdr = off_rows + pad16(n_copies * 8);
+        // L2 prefetch entries behind the copies: the runs of OWN columns of the tile (consecutive owned nodes are
+        // contiguous in both layouts).  The kernels pull every array the consumers load straight from global memory
+        // (fct_adf_v, area, the c-vertical operands, ...) into L2 over these ranges one tile ahead.
+        std::vector<Copy> pfs;
+        for (int i = 0; i < nn;) {
+            int j = i;
+            while (j + 1 < nn && tile_nodes[j + 1] == tile_nodes[j] + 1) ++j;
+            const unsigned g0 = ngoff(tile_nodes[i]);
+            long long bytes = (long long)(ngoff(tile_nodes[j]) - g0) * 8 + (packed ? nbytes(tile_nodes[j]) : P * 8);
+            bytes = std::min<long long>(bytes, 0x3fff * 16);
+            if ((int)pfs.size() < WT_MAX_PREFETCH && bytes >= 16) pfs.push_back({g0, 0, (int)(bytes & ~15LL), 3});
+            i = j + 1;
+        }
+        const int n_pf = (int)pfs.size();
+        const int off_hdr = off_rows + pad16((n_copies + n_pf) * 8);
         const int off_ent = off_hdr + (int)hdr.size() * 16;
         const int off_sched = off_ent + (int)ent.size() * 16;
         const int blob_bytes = off_sched + pad16((int)sched.size() * 2);
@@ -497,10 +511,13 @@ bool build_warptiles(const DerivedHost &d, const int *nlev_n, int N, int NT, int
         h[9] = rb;
         h[10] = eb;
         h[11] = (int)tx;
+        h[12] = n_pf;
         {
             int2 *t = reinterpret_cast<int2 *>(buf.data() + off_rows);
             for (int k = 0; k < n_copies; ++k)
                 t[k] = make_int2((int)copies[k].goff, (copies[k].soff >> 4) | ((copies[k].bytes >> 4) << 14) | (copies[k].arr << 28));
+            for (int k = 0; k < n_pf; ++k)
+                t[n_copies + k] = make_int2((int)pfs[k].goff, ((pfs[k].bytes >> 4) << 14) | (3 << 28));
         }
         if (!hdr.empty()) std::memcpy(buf.data() + off_hdr, hdr.data(), hdr.size() * 16);
         if (!ent.empty()) std::memcpy(buf.data() + off_ent, ent.data(), ent.size() * 16);

@@ -57,7 +57,9 @@ struct WarpTilesDev {
     int opt;                    // scheduling options (results unaffected): 1 producers wait suspended in hardware
                                 // instead of polling, 2 consumers issue a tile's first loads before waiting for its rows,
                                 // 4 copy lists travel ahead of their blobs (needs max_copies <= WT_PRE_MAX_COPIES),
-                                // 8 fetcher and issuers probe a released stage every 40 ns (hand-over on the critical path)
+                                // 8 fetcher and issuers probe a released stage every 40 ns (hand-over on the critical path),
+                                // 16 / 32 / 64 other producer wait modes, 128 the issuers pull the own columns of every array
+                                // the consumers load from global memory into L2, tile by tile
     int max_copies;             // longest copy list of a tile
     long long *trace;           // profiling aid (knob WT_TRACE): SM-clock stamps of the pipeline events of CTA 0,
                                 // WT_TRACE_SLOTS per tile iteration, at most WT_TRACE_ITERS iterations; null: off
@@ -99,6 +101,8 @@ constexpr int WT_SMEM_MAX = 227 * 1024;
 // entry int4: {smem byte offset of the edge row, smem byte offset of the other node's row,
 //              depth | writer << 30 | second << 31, global element offset of the edge row}
 // schedule: one unsigned short per lane: node (8 bits) | level pair (7 bits) << 8 | ghost << 15; 0xffff idle
+//  [12] L2 prefetch entries behind the copy list (array code 3, no shared-memory offset): runs of own columns
+constexpr int WT_MAX_PREFETCH = 8;
 constexpr int WT_HDR_BYTES = 64;
 constexpr int WT_PRE_MAX_COPIES = (WT_PRE_BYTES - WT_HDR_BYTES) / 8;
 constexpr unsigned WT_IDLE = 0xffffu;
@@ -562,7 +566,7 @@ __device__ __forceinline__ WtEarly wt_early(const Arrays &A, const WtView &V, in
             E.a1 = aa.y;
             // the operands of c vertical are consumed after the item's edge loop: pull them into L2
             // now (one probe per 64 bytes) instead of holding 24 registers for loads in flight
-            if (!ITER && (z0 & 7) == 0 && !(A.flags & 1)) {
+            if (!ITER && (z0 & 7) == 0 && !(A.flags & 5)) {   // (bit 4: the issuers prefetch the whole tile, opt 128)
                 prefetch_l2(A.del_v + tn + grow);
                 prefetch_l2(A.del_h + tn + grow);
                 prefetch_l2(A.ttf + tn + grow);
@@ -908,6 +912,33 @@ __device__ __forceinline__ void reg_alloc()
 // tile's item counter ahead of its warp items: the first warps to reach a tile convert it, in parallel and at
 // full issue priority, instead of two converter warps taking 2.2 us of every 4 us refill (WT_TRACE).
 constexpr int WT_CONV_CHUNKS = 16;
+// Tile-level L2 prefetch (WarpTilesDev::opt bit 128): the arrays the consumers load straight from global memory,
+// over the runs of own columns the blob lists behind its copies, one bulk prefetch per (run, array), issued by the
+// issuer warps while the tile is still a tile period away -- instead of one L2 probe per 64 bytes and array issued
+// by every consumer item one item ahead (ncu: a fifth of phase B's stall samples wait for exactly those loads).
+template <bool PHASE_A, bool ITER>
+__device__ __forceinline__ void wt_prefetch_own(const Arrays &A, const int2 *entries, int n_pf, int tr, int idx, int stride)
+{
+    constexpr int NA = PHASE_A ? 2 : 8;
+    for (int u = idx; u < n_pf * NA; u += stride) {
+        const int2 r = entries[u / NA];
+        const uint32_t sz = (((uint32_t)r.y >> 14) & 0x3fffu) << 4;
+        const size_t g = (uint32_t)r.x;
+        const double *p;
+        switch (u % NA) {
+        case 0: p = A.adf_v + tr * A.ts_nodev + g; break;
+        case 1: p = (PHASE_A ? A.area_inv : A.area) + g; break;
+        case 2: p = A.del_v + tr * A.ts_node + g; break;
+        case 3: p = A.del_h + tr * A.ts_node + g; break;
+        case 4: p = A.ttf + tr * A.ts_node + g; break;
+        case 5: p = A.lo + tr * A.ts_node + g; break;
+        case 6: p = A.hnode + g; break;
+        default: p = A.hnode_new + g; break;
+        }
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(sz) : "memory");
+    }
+}
+
 template <bool PHASE_A, int NSTAGE, int NWC, int NPW, bool VLIMIT_ONE = true, bool ITER = false, int RC = 0, int NCV = WT_CONVERTERS>
 __global__ void __launch_bounds__((RC > 0 ? wt_producer_warps(RC) : NPW + 1 + ((PHASE_A && NCV > 0) ? NCV : 0)) * 32 + NWC * 32, 1)
 k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched_ctr)
@@ -1039,6 +1070,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(sz) : "memory");
             }
+            if ((T.opt & 128) && !ITER)
+                wt_prefetch_own<PHASE_A, ITER>(A, copies + n_copies, reinterpret_cast<const int4 *>(pl)[3].x, tr, (warp - 1) * 32 + lane, NPW * 32);
             if (T.opt & 8) mbar_wait_handover(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
             else mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt);
             if (warp == 1) wt_trace(T, it, 2);
@@ -1076,6 +1109,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 if (T.diag == 0 || (T.diag == 1 && arr != 2)) bulk_g2s(sa + so, src, sz, b_rows(s));
             }
+            if ((T.opt & 128) && !ITER)
+                wt_prefetch_own<PHASE_A, ITER>(A, V.copies + V.n_copies, reinterpret_cast<const int4 *>(V.blob)[3].x, tr, (warp - 1) * 32 + lane, NPW * 32);
             if (warp == 1) wt_trace(T, it, 3);
             __syncwarp();
         }
