@@ -469,10 +469,10 @@ bool launch_warp(int stage, const Arrays &A, const Plan *p, int which, int ntrac
     // measured (profiles/r1_v11_sched_options_sweep_mid.log, r1_v14_ab_ring_depth.log): first loads before
     // the rows wait (2) is +10 % on phase A; lists ahead (4) pays with a two-stage ring only; suspended
     // producers (1) are neutral
-    // round 2 (profiles/r2_v21_*): the issuers pull the own columns of the arrays the consumers load from global memory
-    // into L2 tile by tile (128): phase A +1..3 %, phase B +3 % with three stages, -1 % with two (there the per-item
-    // probes of the consumers stay)
-    if (T.opt < 0) T.opt = 2 | (stages == 2 ? 4 : 0) | ((isA || stages != 2) ? 128 : 0);
+    // round 2 (profiles/r2_v21_*, r2_v23_*): the issuers pull the own columns of the arrays the consumers load from global
+    // memory into L2 tile by tile (128): phase A +1..3 %, phase B +3 % with three stages; with two stages (lists ahead)
+    // phase B wants it ONE tile period ahead, after the stage's own copies (256): +7 %, two periods ahead: -1 %
+    if (T.opt < 0) T.opt = 2 | (stages == 2 ? 4 : 0) | 128 | ((!isA && stages == 2) ? 256 : 0);
     if (T.max_copies > WT_PRE_MAX_COPIES || T.diag != 0) T.opt &= ~4;
     if (WT_SMEM_HEAD + (size_t)stages * stage_bytes > (size_t)WT_SMEM_MAX) {
         std::fprintf(stderr, "fesom2-accelerate: warp tiles of %d B do not fit two stages\n", stage_bytes);

@@ -59,7 +59,8 @@ struct WarpTilesDev {
                                 // 4 copy lists travel ahead of their blobs (needs max_copies <= WT_PRE_MAX_COPIES),
                                 // 8 fetcher and issuers probe a released stage every 40 ns (hand-over on the critical path),
                                 // 16 / 32 / 64 other producer wait modes, 128 the issuers pull the own columns of every array
-                                // the consumers load from global memory into L2, tile by tile
+                                // the consumers load from global memory into L2, tile by tile (with lists ahead: two tile
+                                // periods ahead, or one with 256)
     int max_copies;             // longest copy list of a tile
     long long *trace;           // profiling aid (knob WT_TRACE): SM-clock stamps of the pipeline events of CTA 0,
                                 // WT_TRACE_SLOTS per tile iteration, at most WT_TRACE_ITERS iterations; null: off
@@ -1070,7 +1071,7 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(sz) : "memory");
             }
-            if ((T.opt & 128) && !ITER)
+            if ((T.opt & 384) == 128 && !ITER)   // two tile periods ahead (with the rows) ...
                 wt_prefetch_own<PHASE_A, ITER>(A, copies + n_copies, reinterpret_cast<const int4 *>(pl)[3].x, tr, (warp - 1) * 32 + lane, NPW * 32);
             if (T.opt & 8) mbar_wait_handover(b_empty(s), ((it / NSTAGE) & 1) ^ 1);
             else mbar_wait_idle(b_empty(s), ((it / NSTAGE) & 1) ^ 1, T.opt);
@@ -1084,6 +1085,8 @@ k_phase_warp(Arrays A, WarpTilesDev T, int ntracers, int stage_bytes, int *sched
                 const double *src = (arr == 0 ? ga : (arr == 1 ? gb : ge)) + (uint32_t)r.x;
                 bulk_g2s(sa + so, src, sz, b_rows(s));
             }
+            if ((T.opt & 384) == 384 && !ITER)   // ... or (bit 256) one tile period ahead, after the stage's own copies
+                wt_prefetch_own<PHASE_A, ITER>(A, copies + n_copies, reinterpret_cast<const int4 *>(pl)[3].x, tr, (warp - 1) * 32 + lane, NPW * 32);
             if (warp == 1) wt_trace(T, it, 3);
             __syncwarp();
             if (lane == 0) mbar_arrive(b_prefree(s));
