@@ -24,11 +24,13 @@
 //     columns first, halo columns, edge rows by ascending id, so rows that are adjacent in global
 //     memory are adjacent in shared memory and travel as ONE copy: about 40 copies per tile in the
 //     packed storage, 240 in the padded layout, where a single issuer warp was the bottleneck
-//     (profiles/r1_v3_*).  In phase A two more warps turn the landed (fct_LO, ttf) rows in place
-//     into the a1 bounds of reference.cpp:315-316.  NWC consumer warps draw warp items of the ready
-//     stage from a shared counter, so tiles k+1 and k+2 are in flight while tile k is computed, and
-//     every item loads the first-needed own-column values of the warp's NEXT item before its own
-//     edge loop.
+//     (profiles/r1_v3_*).  The a1 bounds of reference.cpp:315-316 are taken on the fly in phase A's
+//     edge loop from the raw (fct_LO, ttf) rows (round 2; two converter warps that rewrite the landed
+//     rows in place remain for the vlimit 2 / 3 variants).  The issuer warps also pull the own columns
+//     of every array the consumers load straight from global memory into L2, tile by tile.  NWC
+//     consumer warps draw warp items of the ready stage from a shared counter, so tiles k+1 and k+2
+//     are in flight while tile k is computed, and every item loads the first-needed own-column
+//     values of the warp's NEXT item before its own edge loop.
 //   * A warp item is 32 lanes, each a (node, pair of ACTIVE levels) slot; consecutive lanes hold
 //     consecutive slots of a node, so the vertical 3-point stencil of a3 is two warp shuffles.  A
 //     column that does not fit the rest of an item is split, with one GHOST slot on either side of
@@ -76,9 +78,9 @@ __device__ __forceinline__ void wt_trace(const WarpTilesDev &T, int it, int slot
         T.trace[it * WT_TRACE_SLOTS + slot] = clock64();
 }
 
-// warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A WT_CONVERTERS a1 converters, then NWC
-// consumers (registers are granted as if the CTA had a multiple of 4 warps: 16 warps -> 128 per
-// thread, 20 -> 96, 24 -> 80)
+// warp roles: 0 blob fetcher, 1..NPW copy issuers, in phase A NCV a1 converters (0 in the default shape:
+// a1 is folded into the consumers), then NWC consumers (registers are granted as if the CTA had a
+// multiple of 4 warps: 16 warps -> 128 per thread, 20 -> 96, 24 -> 80)
 // Head of a blob (header + copy list) copied ahead of the blob itself into a slot of its own, one
 // per stage: the issuer warps pull the tile's rows into L2 while the stage is still being computed
 // and start the bulk copies the moment it is released, next to the blob's copy instead of after it.
