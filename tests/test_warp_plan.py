@@ -503,3 +503,45 @@ def test_unstructured_delaunay_mesh_packed(mesh_mod, abi, oracle_mod, tn, cap):
     pk = Packed(m)
     g, P = emulate(m, f, blob, off, nt, packed=pk)
     compare_packed(m, f, g, pk, want)
+
+
+@pytest.mark.parametrize("packed", [0, 1])
+def test_l2_prefetch_entries_cover_the_own_columns(mesh_mod, abi, packed):
+    """Behind its bulk copies every tile's blob lists the runs of its OWN columns (array code 3, no shared-memory
+    offset): what the issuer warps pull into L2 for the arrays the consumers load straight from global memory.
+    The runs must be 16-byte granular, disjoint, inside the tile's columns and together cover them (up to the cap
+    of eight runs per tile) -- for the contiguous tiles of a single domain and the scattered ones of a boundary set."""
+    gm = mesh_mod.make_workload("pi")
+    for m, which in ((gm, 0), (mesh_mod.partition_mesh(gm, 3, ranks=[1])[0].mesh, 1), (mesh_mod.partition_mesh(gm, 3, ranks=[1])[0].mesh, 2)):
+        st, nt, smem, blob, off = inspect(abi, m, 40, 74 * 1024, which=which, packed=packed)
+        assert st == 0 and nt > 0
+        P = (m.nl + 7) & ~7
+        nz = np.maximum(m.nlevels_nod2D.astype(np.int64) - 1, 0)
+        slots = ((nz + 2) & ~1) if packed else np.full(nz.shape, P)
+        ncol = np.concatenate([[0], np.cumsum(slots)])
+        covered_all = 0
+        for t in range(nt):
+            b = blob[off[t] * 4: off[t + 1] * 4].tobytes()
+            h = np.frombuffer(b, np.int32, 16)
+            n_copies, n_nodes, n_pf, off_hdr = int(h[0]), int(h[2]), int(h[12]), int(h[5])
+            assert 1 <= n_pf <= 8
+            ent = np.frombuffer(b, np.uint32, 2 * (n_copies + n_pf), 64).reshape(-1, 2)[n_copies:]
+            hdr = np.frombuffer(b, np.uint32, 4 * n_nodes, off_hdr).reshape(-1, 4)
+            own0 = hdr[:, 0].astype(np.int64)                                  # global element offset of every own column
+            node = np.searchsorted(ncol, own0, side="right") - 1
+            assert (ncol[node] == own0).all() and (node < m.myDim_nod2D).all()
+            cells = np.zeros(int(ncol[-1]) + P, bool)
+            for g, pk in ent:
+                pk = int(pk)
+                assert (pk >> 28) & 3 == 3 and (pk & 0x3fff) == 0
+                n = ((pk >> 14) & 0x3fff) * 2                                   # doubles
+                assert n > 0 and int(g) % 2 == 0 and not cells[int(g): int(g) + n].any()
+                cells[int(g): int(g) + n] = True
+            own = np.zeros_like(cells)
+            for k in node:
+                own[ncol[k]: ncol[k + 1]] = True
+            assert not (cells & ~own).any()                                     # nothing but own columns
+            if n_pf < 8:
+                assert (cells == own).all()                                     # all of them, unless the cap cut the list
+            covered_all += int(n_pf < 8)
+        assert covered_all >= (nt if which == 0 else 1)
