@@ -398,7 +398,8 @@ struct WarpVariant {
     bool phase_a;
     int stages, consumers, issuers;
     int regs = 0;   // > 0: roles re-allocate registers (setmaxnreg): 4 producer warps + consumers at `regs` each
-    int conv = 2;   // phase A: dedicated converter warps; 0: the consumer warps convert (pipeline v2)
+    int conv = 2;   // phase A: dedicated converter warps (2, 3, 4); 0: the consumer warps run the a1 pass in chunks;
+                    // -1: a1 folded into the consumers' edge loop (the default shape since round 2)
 };
 // total warps (1 fetcher + issuers + [converter] + consumers) a multiple of 4: see fct_warp_kernels.cuh
 #define WT_VA(S, C, I) {k_phase_warp<true, S, C, I>, true, S, C, I}
